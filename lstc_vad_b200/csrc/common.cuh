@@ -1,0 +1,131 @@
+// Shared device/host helpers for the lstc_vad_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// ---- status codes returned through the C-ABI (include/lstc_vad_b200.h) ----
+#define LSTC_OK 0
+#define LSTC_ERR_INVALID_ARG 1
+#define LSTC_ERR_CUDA 2
+#define LSTC_ERR_UNSUPPORTED 3
+#define LSTC_ERR_DRIVER 4
+
+namespace lstc {
+
+void set_last_error(const char* fmt, ...);
+
+#define LSTC_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      ::lstc::set_last_error(__VA_ARGS__);                          \
+      return LSTC_ERR_INVALID_ARG;                                  \
+    }                                                               \
+  } while (0)
+
+#define LSTC_CHECK_CUDA(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::lstc::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                    \
+      return LSTC_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define LSTC_CHECK_LAUNCH() LSTC_CHECK_CUDA(cudaGetLastError())
+
+int num_sms();  // SM count of the current device (cached per device)
+
+// ---------------------------------------------------------------------------
+// bf16 <-> fp32 packing helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16lo_to_f32(v.x); f[1] = bf16hi_to_f32(v.x);
+  f[2] = bf16lo_to_f32(v.y); f[3] = bf16hi_to_f32(v.y);
+  f[4] = bf16lo_to_f32(v.z); f[5] = bf16hi_to_f32(v.z);
+  f[6] = bf16lo_to_f32(v.w); f[7] = bf16hi_to_f32(v.w);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Counter-based dropout RNG: Philox4x32-10.  One call yields 128 random bits =
+// eight 16-bit lanes, i.e. the keep/drop decision for 8 consecutive elements.
+// The mask of element (row, col) of a [rows, ld8*8] grid depends only on
+// (seed, offset, row*ld8 + col/8) so forward and backward kernels regenerate
+// the same mask without storing it (reference keeps masks inside autograd:
+// nn.Dropout at models/MultiHeadAttention.py:46,50, models/FFN.py:11).
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t offset, uint64_t idx,
+                                                       uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// threshold in 1/65536 units: element is DROPPED when its 16-bit lane < thr.
+__host__ __device__ __forceinline__ uint32_t dropout_threshold16(float p) {
+  float t = p * 65536.0f + 0.5f;
+  if (t < 0.f) t = 0.f;
+  if (t > 65535.f) t = 65535.f;
+  return (uint32_t)t;
+}
+
+// 8-bit keep mask (bit j set => element 8*idx8 + j is kept)
+__host__ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t idx8,
+                                                           uint32_t thr16) {
+  uint32_t r[4];
+  philox4x32_10(seed, offset, idx8, r);
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m |= ((r[j] & 0xffffu) >= thr16 ? 1u : 0u) << (2 * j);
+    m |= ((r[j] >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+  }
+  return m;
+}
+
+}  // namespace lstc

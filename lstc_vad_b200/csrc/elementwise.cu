@@ -1,0 +1,443 @@
+// Bandwidth-bound glue kernels: dtype casts, CLS-token prepend (+ absolute position encoding),
+// column sums (bias gradients), dropout apply / mask dump, relative-position bias gather/scatter,
+// device-scalar scaling and the fused Adagrad update.
+#include "common.cuh"
+#include "../../include/lstc_vad_b200.h"
+
+namespace lstc {
+namespace ew {
+
+static inline unsigned grid_for(int64_t work_items, int threads, int per_sm = 8) {
+  int64_t g = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// ---------------------------------------------------------------- casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t n8 = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<uint4*>(dst)[i] = pack8(f);
+  }
+  for (int64_t i = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16(src[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t n8 = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    float f[8];
+    unpack8(v, f);
+    reinterpret_cast<float4*>(dst)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  for (int64_t i = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __bfloat162float(src[i]);
+}
+
+// ---------------------------------------------------------------- CLS prepend
+// grid = (W, ceil(D/8/blockDim)); thread owns 8 columns of one window and walks over its tokens.
+template <bool X_F32>
+__global__ void cls_prepend_fwd_kernel(const void* __restrict__ x, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float drop_scale, uint32_t thr16,
+                                       uint64_t seed, uint64_t offset, int use_drop,
+                                       __nv_bfloat16* __restrict__ out, int64_t L0, int64_t D) {
+  const int64_t w = blockIdx.x;
+  const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c >= D) return;
+  const int64_t L = L0 + 1;
+  const int64_t d8 = D >> 3;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto emit = [&](int64_t l, float (&v)[8]) {
+    if (pos != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pos + l * D + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(pos + l * D + c + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (use_drop) {
+      const uint32_t keep = dropout_keep8(seed, offset, (uint64_t)((w * L + l) * d8 + (c >> 3)), thr16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * drop_scale : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + (w * L + l) * D + c) = pack8(v);
+  };
+  for (int64_t l = 0; l < L0; ++l) {
+    float v[8];
+    if (X_F32) {
+      const float* px = reinterpret_cast<const float*>(x) + (w * L0 + l) * D + c;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(px));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(px + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + (w * L0 + l) * D + c)), v);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    emit(l + 1, v);
+  }
+  float v[8];
+  if (cls != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(cls + c + j);
+  } else {
+    const float inv = 1.0f / (float)L0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j] * inv;
+  }
+  emit(0, v);
+}
+
+// g [W, L, D] bf16 -> dx [W, L0, D] fp32 ; optional atomics into dcls [D] / dpos [L, D] (rarely used paths)
+__global__ void cls_prepend_bwd_kernel(const __nv_bfloat16* __restrict__ g, int cls_learned, float drop_scale,
+                                       uint32_t thr16, uint64_t seed, uint64_t offset, int use_drop,
+                                       float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
+                                       int64_t L0, int64_t D) {
+  const int64_t w = blockIdx.x;
+  const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c >= D) return;
+  const int64_t L = L0 + 1;
+  const int64_t d8 = D >> 3;
+  auto fetch = [&](int64_t l, float (&v)[8]) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(g + (w * L + l) * D + c)), v);
+    if (use_drop) {
+      const uint32_t keep = dropout_keep8(seed, offset, (uint64_t)((w * L + l) * d8 + (c >> 3)), thr16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * drop_scale : 0.f;
+    }
+    if (dpos != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dpos + l * D + c + j, v[j]);
+    }
+  };
+  float g0[8];
+  fetch(0, g0);
+  if (cls_learned) {
+    if (dcls != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dcls + c + j, g0[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g0[j] = 0.f;
+  } else {
+    const float inv = 1.0f / (float)L0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g0[j] *= inv;
+  }
+  for (int64_t l = 0; l < L0; ++l) {
+    float v[8];
+    fetch(l + 1, v);
+    if (dx != nullptr) {
+      float* p = dx + (w * L0 + l) * D + c;
+      *reinterpret_cast<float4*>(p) = make_float4(v[0] + g0[0], v[1] + g0[1], v[2] + g0[2], v[3] + g0[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(v[4] + g0[4], v[5] + g0[5], v[6] + g0[6], v[7] + g0[7]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- column sum
+// block (32, 8): threadIdx.x -> 8 columns each (256 columns per block), threadIdx.y -> row lane.
+__global__ void colsum_stage1_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                     float* __restrict__ partial /*[gridDim.y][cols]*/) {
+  __shared__ float red[8][32][9];
+  const int64_t c = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < cols) {
+    const bool vec = (c + 8 <= cols) && (ld % 8 == 0);
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
+      if (vec) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * ld + c)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      } else {
+        for (int j = 0; j < 8 && c + j < cols; ++j) acc[j] += __bfloat162float(x[r * ld + c + j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][j];
+      if (c + j < cols) partial[(int64_t)blockIdx.y * cols + c + j] = s;
+    }
+  }
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nparts, int64_t cols,
+                                     float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * cols + c];
+  out[c] = s;
+}
+static int colsum_parts(int64_t rows) {
+  int64_t p = (rows + 63) / 64;
+  if (p > 128) p = 128;
+  if (p < 1) p = 1;
+  return (int)p;
+}
+
+// ---------------------------------------------------------------- dropout helpers
+__global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                     int64_t n8, float scale, uint32_t thr16, uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+    const uint32_t keep = dropout_keep8(seed, offset, (uint64_t)i, thr16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * scale : 0.f;
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+}
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t rows, int64_t cols, uint32_t thr16,
+                                    uint64_t seed, uint64_t offset) {
+  const int64_t ld8 = (cols + 7) >> 3;
+  const int64_t total = rows * ld8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / ld8, c8 = i % ld8;
+    const uint32_t keep = dropout_keep8(seed, offset, (uint64_t)i, thr16);
+    for (int j = 0; j < 8 && c8 * 8 + j < cols; ++j) mask[r * cols + c8 * 8 + j] = (uint8_t)((keep >> j) & 1u);
+  }
+}
+
+// ---------------------------------------------------------------- rel-pos bias
+__global__ void relbias_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ index,
+                                      int64_t index_ld, int L, int H, int64_t T, float* __restrict__ dense) {
+  const int64_t total = (int64_t)H * L * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / ((int64_t)L * L));
+    const int r = (int)((i / L) % L), c = (int)(i % L);
+    float v = 0.f;
+    if (r > 0 && c > 0) {
+      const int64_t t = index[(int64_t)(r - 1) * index_ld + (c - 1)];
+      if (t >= 0 && t < T) v = table[t * H + h];
+    }
+    dense[i] = v;
+  }
+}
+__global__ void relbias_scatter_kernel(const float* __restrict__ ddense, const int64_t* __restrict__ index,
+                                       int64_t index_ld, int L, int H, int64_t T, float* __restrict__ dtable) {
+  const int64_t total = (int64_t)H * L * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / ((int64_t)L * L));
+    const int r = (int)((i / L) % L), c = (int)(i % L);
+    if (r > 0 && c > 0) {
+      const int64_t t = index[(int64_t)(r - 1) * index_ld + (c - 1)];
+      if (t >= 0 && t < T) atomicAdd(dtable + t * H + h, ddense[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- misc
+__global__ void scale_by_scalar_kernel(const float* __restrict__ src, const float* __restrict__ scalar,
+                                       float* __restrict__ dst, int64_t n) {
+  const float s = __ldg(scalar);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * s;
+}
+__global__ void threshold_kernel(const float* __restrict__ s, float thr, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = s[i];
+    out[i] = v > thr ? v : 0.f;
+  }
+}
+// torch.optim.Adagrad (lr_decay = 0): g = grad*grad_scale + wd*p ; sum += g*g ; p -= lr * g / (sqrt(sum)+eps)
+__global__ void adagrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ st, int64_t n,
+                               float lr, float wd, float eps, float gscale) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 sv = reinterpret_cast<float4*>(st)[i];
+    float* pp = reinterpret_cast<float*>(&pv);
+    const float* gp = reinterpret_cast<const float*>(&gv);
+    float* sp = reinterpret_cast<float*>(&sv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg = gp[j] * gscale + wd * pp[j];
+      sp[j] += gg * gg;
+      pp[j] -= lr * gg / (sqrtf(sp[j]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(st)[i] = sv;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gg = g[i] * gscale + wd * p[i];
+    st[i] += gg * gg;
+    p[i] -= lr * gg / (sqrtf(st[i]) + eps);
+  }
+}
+
+}  // namespace ew
+}  // namespace lstc
+
+using namespace lstc;
+
+extern "C" int lstc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  LSTC_CHECK_ARG(n == 0 || (src && dst), "lstc_cast_f32_to_bf16: null pointer");
+  LSTC_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "lstc_cast_f32_to_bf16: alignment");
+  if (n == 0) return LSTC_OK;
+  ew::cast_f32_bf16_kernel<<<ew::grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, (__nv_bfloat16*)dst, n);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  LSTC_CHECK_ARG(n == 0 || (src && dst), "lstc_cast_bf16_to_f32: null pointer");
+  LSTC_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "lstc_cast_bf16_to_f32: alignment");
+  if (n == 0) return LSTC_OK;
+  ew::cast_bf16_f32_kernel<<<ew::grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, dst, n);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+extern "C" int lstc_cls_prepend_fwd(const void* x, int x_is_f32, const float* cls, const float* pos, float drop_p,
+                                    uint64_t seed, uint64_t offset, void* out, int64_t W, int64_t L0, int64_t D,
+                                    void* stream) {
+  LSTC_CHECK_ARG(x && out, "lstc_cls_prepend_fwd: null pointer");
+  LSTC_CHECK_ARG(L0 >= 1 && D % 8 == 0 && D > 0, "lstc_cls_prepend_fwd: need L0 >= 1 and D %% 8 == 0");
+  LSTC_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "lstc_cls_prepend_fwd: drop_p out of range");
+  if (W == 0) return LSTC_OK;
+  const int threads = 128;
+  dim3 grid((unsigned)W, (unsigned)((D / 8 + threads - 1) / threads));
+  const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int use_drop = (drop_p > 0.f && pos != nullptr) ? 1 : 0;
+  if (x_is_f32)
+    ew::cls_prepend_fwd_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        x, cls, pos, dscale, dropout_threshold16(drop_p), seed, offset, use_drop, (__nv_bfloat16*)out, L0, D);
+  else
+    ew::cls_prepend_fwd_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        x, cls, pos, dscale, dropout_threshold16(drop_p), seed, offset, use_drop, (__nv_bfloat16*)out, L0, D);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+extern "C" int lstc_cls_prepend_bwd(const void* g, int cls_learned, float drop_p, uint64_t seed, uint64_t offset,
+                                    float* dx, float* dcls, float* dpos, int64_t W, int64_t L0, int64_t D,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LSTC_CHECK_ARG(g != nullptr, "lstc_cls_prepend_bwd: null pointer");
+  LSTC_CHECK_ARG(L0 >= 1 && D % 8 == 0 && D > 0, "lstc_cls_prepend_bwd: need L0 >= 1 and D %% 8 == 0");
+  if (dcls) LSTC_CHECK_CUDA(cudaMemsetAsync(dcls, 0, D * sizeof(float), stream));
+  if (dpos) LSTC_CHECK_CUDA(cudaMemsetAsync(dpos, 0, (L0 + 1) * D * sizeof(float), stream));
+  if (W == 0) return LSTC_OK;
+  const int threads = 128;
+  dim3 grid((unsigned)W, (unsigned)((D / 8 + threads - 1) / threads));
+  const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int use_drop = (drop_p > 0.f && dpos != nullptr) ? 1 : 0;
+  ew::cls_prepend_bwd_kernel<<<grid, threads, 0, stream>>>((const __nv_bfloat16*)g, cls_learned, dscale,
+                                                          dropout_threshold16(drop_p), seed, offset, use_drop, dx,
+                                                          dcls, dpos, L0, D);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+extern "C" int64_t lstc_colsum_workspace(int64_t rows, int64_t cols) {
+  return (int64_t)ew::colsum_parts(rows) * cols * (int64_t)sizeof(float);
+}
+extern "C" int lstc_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* workspace,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LSTC_CHECK_ARG(out && workspace && cols > 0, "lstc_colsum_bf16: null pointer / empty");
+  if (rows == 0) {
+    LSTC_CHECK_CUDA(cudaMemsetAsync(out, 0, cols * sizeof(float), stream));
+    return LSTC_OK;
+  }
+  LSTC_CHECK_ARG(x != nullptr, "lstc_colsum_bf16: null input");
+  const int parts = ew::colsum_parts(rows);
+  dim3 grid((unsigned)((cols + 255) / 256), (unsigned)parts);
+  ew::colsum_stage1_kernel<<<grid, dim3(32, 8), 0, stream>>>((const __nv_bfloat16*)x, rows, cols, ld,
+                                                              (float*)workspace);
+  LSTC_CHECK_LAUNCH();
+  ew::colsum_stage2_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>((const float*)workspace, parts, cols,
+                                                                              out);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+extern "C" int lstc_dropout_apply_bf16(const void* x, void* y, int64_t rows, int64_t cols, float p, uint64_t seed,
+                                       uint64_t offset, void* stream) {
+  LSTC_CHECK_ARG(x && y, "lstc_dropout_apply_bf16: null pointer");
+  LSTC_CHECK_ARG(cols % 8 == 0, "lstc_dropout_apply_bf16: cols must be a multiple of 8");
+  LSTC_CHECK_ARG(p >= 0.f && p < 1.f, "lstc_dropout_apply_bf16: p out of range");
+  const int64_t n8 = rows * cols / 8;
+  if (n8 == 0) return LSTC_OK;
+  ew::dropout_apply_kernel<<<ew::grid_for(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n8, 1.f / (1.f - p), dropout_threshold16(p), seed, offset);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_dropout_mask(uint8_t* mask, int64_t rows, int64_t cols, float p, uint64_t seed,
+                                 uint64_t offset, void* stream) {
+  LSTC_CHECK_ARG(mask != nullptr, "lstc_dropout_mask: null pointer");
+  LSTC_CHECK_ARG(p >= 0.f && p < 1.f, "lstc_dropout_mask: p out of range");
+  if (rows * cols == 0) return LSTC_OK;
+  ew::dropout_mask_kernel<<<ew::grid_for(rows * ((cols + 7) / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      mask, rows, cols, dropout_threshold16(p), seed, offset);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+extern "C" int lstc_relbias_gather(const float* table, const int64_t* index, int64_t index_ld, int L, int H,
+                                   int64_t T, float* dense, void* stream) {
+  LSTC_CHECK_ARG(table && index && dense, "lstc_relbias_gather: null pointer");
+  LSTC_CHECK_ARG(L >= 1 && H >= 1 && index_ld >= L - 1, "lstc_relbias_gather: index buffer smaller than L-1");
+  ew::relbias_gather_kernel<<<ew::grid_for((int64_t)H * L * L, 256), 256, 0, (cudaStream_t)stream>>>(
+      table, index, index_ld, L, H, T, dense);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_relbias_scatter(const float* ddense, const int64_t* index, int64_t index_ld, int L, int H,
+                                    int64_t T, float* dtable, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LSTC_CHECK_ARG(ddense && index && dtable, "lstc_relbias_scatter: null pointer");
+  LSTC_CHECK_ARG(L >= 1 && H >= 1 && index_ld >= L - 1, "lstc_relbias_scatter: index buffer smaller than L-1");
+  LSTC_CHECK_CUDA(cudaMemsetAsync(dtable, 0, T * H * sizeof(float), stream));
+  ew::relbias_scatter_kernel<<<ew::grid_for((int64_t)H * L * L, 256), 256, 0, stream>>>(ddense, index, index_ld, L, H,
+                                                                                       T, dtable);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+extern "C" int lstc_scale_by_device_scalar(const float* src, const float* scalar_dev, float* dst, int64_t n,
+                                           void* stream) {
+  LSTC_CHECK_ARG(n == 0 || (src && scalar_dev && dst), "lstc_scale_by_device_scalar: null pointer");
+  if (n == 0) return LSTC_OK;
+  ew::scale_by_scalar_kernel<<<ew::grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, scalar_dev, dst, n);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_threshold_labels(const float* scores, float thr, float* out, int64_t n, void* stream) {
+  LSTC_CHECK_ARG(n == 0 || (scores && out), "lstc_threshold_labels: null pointer");
+  if (n == 0) return LSTC_OK;
+  ew::threshold_kernel<<<ew::grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(scores, thr, out, n);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, float lr,
+                                 float weight_decay, float eps, float grad_scale, void* stream) {
+  LSTC_CHECK_ARG(n == 0 || (param && grad && state_sum), "lstc_adagrad_step: null pointer");
+  LSTC_CHECK_ARG(((uintptr_t)param % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)state_sum % 16 == 0),
+                 "lstc_adagrad_step: 16-byte alignment");
+  if (n == 0) return LSTC_OK;
+  ew::adagrad_kernel<<<ew::grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, state_sum, n, lr,
+                                                                                      weight_decay, eps, grad_scale);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}

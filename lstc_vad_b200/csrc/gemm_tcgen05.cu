@@ -1,0 +1,603 @@
+// bf16 x bf16 -> fp32 GEMM on the sm_100a 5th-gen tensor cores.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B boxes, 4-6 stage mbarrier ring)
+//   warp 1      : tcgen05.mma issuer (single elected lane), owns the TMEM allocation
+//   warps 2..5  : epilogue (tcgen05.ld TMEM -> registers -> fused bias / ReLU / ReLU-mask /
+//                 dropout / residual add -> global), double-buffered against the MMA warp
+//                 through two TMEM accumulator stages.
+//
+// Operands may be K-major (reduction dim contiguous) or MN-major (reduction dim is the row
+// index), selected per operand, so the three GEMMs of a linear layer need no transposes:
+//   forward  y  = x  W^T      : A = x  [M,K]  K-major,  B = W  [N,K]  K-major
+//   dgrad    dx = dy W        : A = dy [M,N]  K-major,  B = W  [N,K]  MN-major (reduce over N)
+//   wgrad    dW = dy^T x      : A = dy [M,N]  MN-major, B = x  [M,K]  MN-major (reduce over M)
+// This replaces the reference's nn.Linear / F.relu / nn.Dropout / residual-add chains at
+// models/MultiHeadAttention.py:97-99,123-124, models/FFN.py:17-19 and models/Classifier.py:8.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/lstc_vad_b200.h"
+
+namespace lstc {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // one 128-byte swizzle atom of bf16 along the reduction dim
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;     // 6 warps
+constexpr int NUM_EPI_WARPS = 4;
+constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+
+struct EpilogueParams {
+  void* C;                 // bf16 or fp32 [M, N]
+  int64_t ldc;
+  int c_is_f32;
+  int atomic_add;          // fp32 only: red.add into C (split-K)
+  const float* bias;       // [N] or null
+  int relu;
+  const __nv_bfloat16* relu_mask;  // [M,N] : out *= (mask > 0)
+  int64_t ld_mask;
+  const __nv_bfloat16* residual;   // [M,N] : out += residual
+  int64_t ld_res;
+  float drop_p;            // dropout applied before the residual add
+  float drop_scale;
+  uint32_t drop_thr16;
+  uint64_t seed, offset;
+  int64_t drop_ld8;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a broken pipeline traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("lstc gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// Descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
+// ------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor for a SWIZZLE_128B tile written by TMA.
+//   K-major : rows of 64 bf16 (128 B), 8-row groups 1024 B apart  -> SBO = 1024, LBO unused (1)
+//   MN-major: boxes of [64 k][64 mn]; 8-k groups 1024 B apart (SBO), 64-mn groups 8192 B apart (LBO)
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  const uint32_t lbo = MN_MAJOR ? (8192u >> 4) : 1u;
+  const uint32_t sbo = 1024u >> 4;
+  d |= (uint64_t)lbo << 16;
+  d |= (uint64_t)sbo << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Start-address advance (in 16-byte units) for the k-th UMMA_K slice inside a BLOCK_K stage.
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint32_t desc_k_advance(int k) {
+  return MN_MAJOR ? (uint32_t)(k * (UMMA_K * 128 / 16))  // 16 k-rows of 128 B
+                  : (uint32_t)(k * (UMMA_K * 2 / 16));   // 32 B along the swizzled row
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4)                      // D format  : F32
+         | (1u << 7)                    // A format  : BF16
+         | (1u << 10)                   // B format  : BF16
+         | ((A_MN ? 1u : 0u) << 15)     // A major
+         | ((B_MN ? 1u : 0u) << 16)     // B major
+         | ((uint32_t)(BN >> 3) << 17)  // N >> 3
+         | ((uint32_t)(BLOCK_M >> 4) << 24);  // M >> 4
+}
+
+template <int BN>
+struct Config {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM cols");
+};
+
+// ------------------------------------------------------------------------------------------
+// Epilogue math on one 32-column chunk of one accumulator row
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, float (&v)[32], int64_t row,
+                                               int64_t col0, int64_t N) {
+  const bool full = (col0 + 32 <= N);
+  // + bias
+  if (ep.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
+    }
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (ep.relu_mask != nullptr) {
+    const __nv_bfloat16* mrow = ep.relu_mask + row * ep.ld_mask + col0;
+    if (full && (ep.ld_mask % 8 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(mrow + j));
+        float f[8];
+        unpack8(m, f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[j + t] = f[t] > 0.f ? v[j + t] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) v[j] = __bfloat162float(mrow[j]) > 0.f ? v[j] : 0.f;
+    }
+  }
+  if (ep.drop_p > 0.f) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint32_t keep =
+          dropout_keep8(ep.seed, ep.offset, (uint64_t)(row * ep.drop_ld8 + ((col0 + j) >> 3)), ep.drop_thr16);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[j + t] = ((keep >> t) & 1u) ? v[j + t] * ep.drop_scale : 0.f;
+    }
+  }
+  if (ep.residual != nullptr) {
+    const __nv_bfloat16* rrow = ep.residual + row * ep.ld_res + col0;
+    if (full && (ep.ld_res % 8 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(rrow + j));
+        float f[8];
+        unpack8(m, f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[j + t] += f[t];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) v[j] += __bfloat162float(rrow[j]);
+    }
+  }
+  // store
+  if (ep.c_is_f32) {
+    float* crow = reinterpret_cast<float*>(ep.C) + row * ep.ldc + col0;
+    if (ep.atomic_add) {
+      if (full && (ep.ldc % 4 == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v[j]),
+                       "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) atomicAdd(crow + j, v[j]);
+      }
+    } else {
+      if (full && (ep.ldc % 4 == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) crow[j] = v[j];
+      }
+    }
+  } else {
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ldc + col0;
+    if (full && (ep.ldc % 8 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) f[t] = v[j + t];
+        *reinterpret_cast<uint4*>(crow + j) = pack8(f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) crow[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
+  using Cfg = Config<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int64_t tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int64_t tiles_n = (N + BN - 1) / BN;
+  const int64_t num_kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  const int64_t kb_per_split = (num_kb_total + splits - 1) / splits;
+  const int64_t num_work = tiles_m * tiles_n * splits;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp_idx == 1) tmem_alloc(tmem_ptr_slot, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_slot) : "memory");
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+        const int64_t tile = wi % (tiles_m * tiles_n);
+        const int64_t split = wi / (tiles_m * tiles_n);
+        const int32_t m0 = (int32_t)((tile / tiles_n) * BLOCK_M);
+        const int32_t n0 = (int32_t)((tile % tiles_n) * BN);
+        const int64_t kb0 = split * kb_per_split;
+        const int64_t kb1 = (kb0 + kb_per_split < num_kb_total) ? kb0 + kb_per_split : num_kb_total;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int32_t k0 = (int32_t)(kb * BLOCK_K);
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(smem_a(stage) + i * 8192, &tmap_a, full_bar(stage), m0 + i * 64, k0);
+          } else {
+            tma_load_2d(smem_a(stage), &tmap_a, full_bar(stage), k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(smem_b(stage) + i * 8192, &tmap_b, full_bar(stage), n0 + i * 64, k0);
+          } else {
+            tma_load_2d(smem_b(stage), &tmap_b, full_bar(stage), k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
+        const int64_t split = wi / (tiles_m * tiles_n);
+        const int64_t kb0 = split * kb_per_split;
+        const int64_t kb1 = (kb0 + kb_per_split < num_kb_total) ? kb0 + kb_per_split : num_kb_total;
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc<A_MN>(smem_a(stage));
+          const uint64_t db = make_smem_desc<B_MN>(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16(tmem_d, da + desc_k_advance<A_MN>(k), db + desc_k_advance<B_MN>(k), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(acc));  // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    uint32_t it = 0;
+    for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
+      const int64_t tile = wi % (tiles_m * tiles_n);
+      const int64_t split = wi / (tiles_m * tiles_n);
+      const int64_t m0 = (tile / tiles_n) * BLOCK_M;
+      const int64_t n0 = (tile % tiles_n) * BN;
+      const int64_t kb0 = split * kb_per_split;
+      const bool has_k = kb0 < num_kb_total;  // an empty split contributes nothing
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int64_t col0 = n0 + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (row < M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
+          epilogue_chunk(ep, v, row, col0, N);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+    }
+  }
+
+  // teardown
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp_idx == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
+// box = [box_rows, 64 cols], SWIZZLE_128B, zero fill out of bounds.
+static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return LSTC_ERR_DRIVER;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%u",
+                   (int)r, ptr, (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return LSTC_ERR_DRIVER;
+  }
+  return LSTC_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                  int splits, const EpilogueParams& ep, cudaStream_t stream) {
+  using Cfg = Config<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: matrix is [MN, K]; MN-major operand: matrix is [K, MN]
+  rc = A_MN ? make_tmap(&ta, A, K, M, lda, BLOCK_K) : make_tmap(&ta, A, M, K, lda, BLOCK_M);
+  if (rc != LSTC_OK) return rc;
+  rc = B_MN ? make_tmap(&tb, B, K, N, ldb, BLOCK_K) : make_tmap(&tb, B, N, K, ldb, BN);
+  if (rc != LSTC_OK) return rc;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set[64] = {false};  // per instantiation and device; benign race (idempotent)
+  int dev = 0;
+  LSTC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * splits;
+  int grid = num_sms();
+  if (tiles < grid) grid = (int)tiles;
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, splits, ep);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+
+template <int BN>
+static int dispatch_major(int a_mn, int b_mn, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M,
+                          int64_t N, int64_t K, int splits, const EpilogueParams& ep, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (!a_mn && b_mn) return launch<BN, false, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (a_mn && b_mn) return launch<BN, true, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  return launch<BN, true, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+}
+
+}  // namespace gemm
+}  // namespace lstc
+
+using namespace lstc;
+
+extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                              int b_mn_major, int64_t M, int64_t N, int64_t K, void* C, int64_t ldc,
+                              int c_is_f32, const float* bias, int relu, const void* relu_mask, int64_t ld_mask,
+                              const void* residual, int64_t ld_res, float dropout_p, uint64_t seed,
+                              uint64_t offset, int split_k, int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LSTC_CHECK_ARG(A && B && C, "lstc_gemm_bf16: null operand");
+  LSTC_CHECK_ARG(M > 0 && N > 0 && K > 0, "lstc_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M,
+                 (long long)N, (long long)K);
+  LSTC_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0,
+                 "lstc_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16-byte pitch), got %lld %lld",
+                 (long long)lda, (long long)ldb);
+  LSTC_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                 "lstc_gemm_bf16: operands must be 16-byte aligned");
+  LSTC_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "lstc_gemm_bf16: dropout_p out of range");
+  LSTC_CHECK_ARG(split_k >= 1, "lstc_gemm_bf16: split_k must be >= 1");
+  LSTC_CHECK_ARG(!(split_k > 1 || accumulate) || c_is_f32, "lstc_gemm_bf16: split-K / accumulate need fp32 C");
+  LSTC_CHECK_ARG(!(split_k > 1) || (!bias && !relu && !relu_mask && !residual && dropout_p == 0.f),
+                 "lstc_gemm_bf16: split-K supports no fused epilogue");
+  LSTC_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "lstc_gemm_bf16: dims exceed int32");
+
+  gemm::EpilogueParams ep;
+  ep.C = C;
+  ep.ldc = ldc;
+  ep.c_is_f32 = c_is_f32;
+  ep.atomic_add = (split_k > 1 || accumulate) ? 1 : 0;
+  ep.bias = bias;
+  ep.relu = relu;
+  ep.relu_mask = (const __nv_bfloat16*)relu_mask;
+  ep.ld_mask = ld_mask;
+  ep.residual = (const __nv_bfloat16*)residual;
+  ep.ld_res = ld_res;
+  ep.drop_p = dropout_p;
+  ep.drop_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  ep.drop_thr16 = dropout_threshold16(dropout_p);
+  ep.seed = seed;
+  ep.offset = offset;
+  ep.drop_ld8 = (N + 7) / 8;
+
+  const int64_t num_kb = (K + gemm::BLOCK_K - 1) / gemm::BLOCK_K;
+  int splits = split_k;
+  if (splits > num_kb) splits = (int)num_kb;
+  if (splits > 1 && !accumulate) {
+    // split-K partial sums are reduced with red.add: start from zero
+    LSTC_CHECK_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, stream));
+  }
+  if (N > 128) return gemm::dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (N > 64) return gemm::dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, ep, stream);
+  return gemm::dispatch_major<64>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, ep, stream);
+}
