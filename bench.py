@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: windows/sec, forward + backward of the LTN train step (ShanghaiTech shape: part_len 3 x
+16 patches, d_model 2048, n_hidden 4096, 3 layers, 8 heads, rel-pos bias; B = 40 video pairs x 16 windows =
+1280 windows per step per GPU) — BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ltn_sht]
+
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL); per-GPU work is fixed
+(weak scaling), bags are sharded by video pair, gradients are all-reduced in buckets overlapped with backward.
+Rank 0 prints ONE JSON line.  `--impl reference` times the CPU port of the reference path (oracle/) on the
+host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "windows/sec fwd+bwd (LTN, d_model 2048)"
+UNIT = "windows/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tflops_sustained=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                    tflops_burst=float(d.get("bf16_tflops", 1590.0)), hbm_gbs=float(d.get("hbm_gbs", 6650.0)),
+                    source="MEASURED_PEAKS.json")
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, timed on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_windows_per_sec(wl, sample_windows: int, steps: int, warmup: int):
+    """fwd + losses + bwd of the reference algorithm (fp32, train-step math, dropout off) on `sample_windows`
+    windows of the workload.  Returns (windows/s from the best step, cores, description)."""
+    import torch
+    from oracle import lstc_oracle as O
+    from lstc_vad_b200.harness import synthetic_step_inputs
+    from lstc_vad_b200.models import Classifier, Encoder  # constructors only (parameter init on CPU)
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = wl.part_num
+    B = max(1, sample_windows // (2 * P))
+    torch.manual_seed(0)
+    enc = Encoder(**wl.encoder_kwargs())
+    cls = Classifier(wl.d_model, 0.6)
+    esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    csd = {k: v.clone().requires_grad_(True) for k, v in cls.state_dict().items()}
+    cfg = O.EncoderConfig(**{k: v for k, v in wl.encoder_kwargs().items() if k in O.EncoderConfig.__dataclass_fields__})
+    feats, labs = synthetic_step_inputs(wl, seed=0, batch_size=B)
+    W = feats.shape[0]
+    times = []
+    for i in range(warmup + steps):
+        for t in list(esd.values()) + list(csd.values()):
+            t.grad = None
+        t0 = time.perf_counter()
+        loss, _ = O.ltn_train_loss(esd, csd, feats, labs, cfg, B, P)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    best = min(times)
+    return W / best, cores, f"{W} windows ({B} video pairs x {P} windows x 2) of {wl.name}, fp32, fwd+loss+bwd, " \
+                           f"best of {steps} steps after {warmup} warm-up, {cores} threads", times
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    wps, cores, sample, times = cpu_reference_windows_per_sec(wl, 32, steps, warmup)
+    ms = 1e3 * sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": wps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl.name}: LTN train step fwd+bwd, part_len {wl.part_len} x {wl.n_patch} patches, "
+                               f"d_model {wl.d_model}, n_hidden {wl.d_inner}, CPU port of the reference path"},
+        "cpu_baseline": {"value": wps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": wps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="ltn_sht")
+    ap.add_argument("--batch-size", type=int, default=None, help="video pairs per GPU per step (default: reference's 40)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true", help="dropout off (default: train mode like the reference)")
+    args = ap.parse_args()
+
+    from lstc_vad_b200.harness import WORKLOADS
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from lstc_vad_b200 import ops
+    from lstc_vad_b200.harness import TrainStep, synthetic_step_inputs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback (use --impl reference)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    warmup = max(args.warmup, 3)
+    steps = args.steps
+    B = args.batch_size or wl.batch_size
+
+    step = TrainStep(wl, dev, seed=0, train_mode=not args.eval_mode, process_group=pg)
+    W = 2 * B * wl.part_num
+    # two distinct host batches (pinned) — rank-dependent seeds; resident device copies for the kernel-side number
+    host = [synthetic_step_inputs(wl, seed=100 + 10 * rank + i, batch_size=B, pin=True) for i in range(2)]
+    resident = [(f.to(dev), l.to(dev)) for f, l in host]
+    in_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 4
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- warm-up (also builds the bf16 weight cache, NCCL channels, bucket plan) ----------------
+    for i in range(warmup):
+        step.zero_grad()
+        f, l = resident[i % 2]
+        step.forward_backward(f, l, B)
+    sync_all()
+
+    # ---------------- device-resident timing (value) with per-GEMM events (roofline) ----------------
+    ops.PROFILE.enable()
+    ops.LAUNCHES.reset()
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step.zero_grad()
+            f, l = resident[i % 2]  # 2 x 0.5 GB inputs + ~9 GB of activations per step: far larger than the 126 MB L2
+            step.forward_backward(f, l, B)
+        e1.record()
+        sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES.count
+    gemm_prof = ops.PROFILE.collect()
+    ops.PROFILE.disable()
+
+    # ---------------- end-to-end: pinned host inputs, H2D each step (double-buffered), D2H of the loss -------------
+    copy_stream = torch.cuda.Stream()
+    dbuf = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            dbuf[s][0].copy_(host[s][0], non_blocking=True)
+            dbuf[s][1].copy_(host[s][1], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record()
+    loss_host = torch.empty(1, pin_memory=True)
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    prefetch(0)
+    d2h = 0
+    for i in range(steps):
+        if i + 1 < steps:
+            prefetch(i + 1)
+        s = i % 2
+        torch.cuda.current_stream().wait_event(ready[s])
+        step.zero_grad()
+        terms = step.forward_backward(dbuf[s][0], dbuf[s][1], B)
+        consumed[s].record()
+        loss_host.copy_(terms["loss"].detach().reshape(1), non_blocking=False)  # D2H read of the step's result
+        d2h = 4
+    t1.record()
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1)
+
+    # ---------------- reduce over ranks: max time ----------------
+    times = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = times.tolist()
+    total_windows = W * steps * world
+    value = total_windows / (ms_total * 1e-3)
+    e2e = total_windows / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        # roofline of the dominant kernel family: the tcgen05 GEMM (all launches in the timed region)
+        flops = sum(r["flops"] for r in gemm_prof)
+        gms = sum(r["ms"] for r in gemm_prof)
+        achieved = flops / (gms * 1e-3) / 1e12 if gms > 0 else None
+        by_kind = {}
+        for r in gemm_prof:
+            k = by_kind.setdefault(r["kind"], {"flops": 0.0, "ms": 0.0, "launches": 0})
+            k["flops"] += r["flops"]; k["ms"] += r["ms"]; k["launches"] += 1
+        for k in by_kind.values():
+            k["tflops"] = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else None
+            k["share_of_step"] = k["ms"] / ms_total
+            del k["flops"]
+        model_tflops = wl.fwd_flops_per_window() * 3 * W * steps / (ms_total * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: LTN train step fwd+bwd (Encoder 3 layers + Classifier + MIL + CE), "
+                                   f"part_len {wl.part_len} x {wl.n_patch} patches, d_model {wl.d_model}, n_hidden "
+                                   f"{wl.d_inner}, {B} video pairs x {wl.part_num} windows x 2 = {W} windows/step/GPU",
+                       "train_mode_dropout": not args.eval_mode, "optimizer_in_timed_region": False,
+                       "l2_policy": "inputs+activations per step (~10 GB) exceed the 126 MB L2; two input batches alternate",
+                       "parallelism": f"dp{world} (bags sharded by video pair)" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["tflops_sustained"]) if achieved else None, "traffic": None,
+                         "kernel": "gemm_bf16_tcgen05_kernel (all launches of the timed region)",
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained", "gemm_share_of_step": gms / ms_total,
+                         "by_operand_layout": by_kind, "model_tflops_whole_step": model_tflops},
+            "clocks": clocks.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            wps, cores, sample, _ = cpu_reference_windows_per_sec(wl, 32, 3, 1)
+            line["cpu_baseline"] = {"value": wps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

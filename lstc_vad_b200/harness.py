@@ -1,0 +1,397 @@
+"""Batched drivers around the drop-in modules: the LTN / STN train step (forward + losses + backward
+[+ fused Adagrad]), data-parallel sharding by video pair with an overlapped bucketed gradient all-reduce,
+and sharded, batched pseudo-label generation / scoring (no collective).
+
+These replace the *loops* of the reference scripts (Train/temporal_transformer_shanghaitech.py:99-144 train
+step, :163-226 and Train/pseudo_labels_generator_temporal.py:113-143 one-window-per-forward sweeps); the
+scripts themselves keep working unmodified on lstc_vad_b200.models.
+"""
+from __future__ import annotations
+
+import math
+import types
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import functional as Fn
+from . import losses, ops
+from .models import Classifier, Encoder, Regressor
+
+# --------------------------------------------------------------------------------------------------
+# workload configurations named by BASELINE.json (shapes: SURVEY.md §8 table)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class Workload:
+    name: str
+    d_model: int
+    d_inner: int
+    part_len: int          # T clips per window
+    n_patch: int           # N tokens per clip
+    part_num: int          # P windows per video
+    batch_size: int        # B video pairs per step
+    relative_pe: bool = True
+    window_size: int = 4
+    MHA_layerNorm: bool = True
+    FFN_layerNorm: bool = True
+    kind: str = "ltn"      # "ltn" (Classifier, MIL + CE) or "stn" (Regressor, MIL)
+    n_layers: int = 3
+    n_head: int = 8
+    d_k: int = 256
+    dropouts: Tuple[float, float, float, float] = (0.2, 0.2, 0.1, 0.6)  # attn, fc, ffn, head
+
+    @property
+    def tokens_per_window(self) -> int:
+        return (self.part_len if self.kind == "ltn" else 1) * self.n_patch
+
+    @property
+    def windows_per_step(self) -> int:
+        w = 2 * self.batch_size * self.part_num
+        return w if self.kind == "ltn" else w * self.part_len
+
+    def encoder_kwargs(self) -> dict:
+        a, f, n, _ = self.dropouts
+        return dict(n_layers=self.n_layers, n_head=self.n_head, d_k=self.d_k, d_v=self.d_k, d_model=self.d_model,
+                    d_inner=self.d_inner, MHA_attn_dropout=a, MHA_fc_dropout=f, MHA_layerNorm=self.MHA_layerNorm,
+                    FFN_dropout=n, FFN_layerNorm=self.FFN_layerNorm, weight_init=(self.kind == "stn"),
+                    relative_pe=self.relative_pe and self.kind == "ltn", window_size=self.window_size,
+                    window_depth=self.part_len)
+
+    def fwd_flops_per_window(self) -> float:
+        """Algorithmic forward FLOPs per window: per layer 2L*D*3*HD + 4*H*L^2*dk + 2L*HD*D +
+        4L*D*Dh, plus the head 2(512 D + 16384 + 32 C)."""
+        L = self.tokens_per_window + 1
+        D, Dh, H, dk = self.d_model, self.d_inner, self.n_head, self.d_k
+        HD = H * dk
+        layer = 2 * L * D * 3 * HD + 4 * H * L * L * dk + 2 * L * HD * D + 4 * L * D * Dh
+        return self.n_layers * layer + 2 * (512 * D + 512 * 32 + 32 * 2)
+
+
+WORKLOADS: Dict[str, Workload] = {
+    # configs[1] of BASELINE.json: LTN train step at the ShanghaiTech shape — the headline configuration
+    "ltn_sht": Workload("ltn_sht", 2048, 4096, 3, 16, 16, 40),
+    "ltn_ucf": Workload("ltn_ucf", 2048, 4096, 2, 9, 32, 40),
+    "ltn_ubnormal": Workload("ltn_ubnormal", 1024, 4096, 5, 16, 16, 40),
+    "stn_sht": Workload("stn_sht", 2048, 3027, 7, 16, 16, 40, relative_pe=False, MHA_layerNorm=False, kind="stn",
+                        dropouts=(0.1, 0.1, 0.3, 0.6)),
+}
+
+
+def synthetic_step_inputs(wl: Workload, seed: int = 0, batch_size: Optional[int] = None, device="cpu",
+                          pin: bool = False):
+    """Non-negative heavy-tailed features (I3D features are post-ReLU) + per-clip pseudo labels.
+    Returns (feats fp32 [W, L0, D] normal windows first, soft labels fp32 [W, 2] | None)."""
+    B = batch_size or wl.batch_size
+    P, T = wl.part_num, wl.part_len
+    W = 2 * B * P * (1 if wl.kind == "ltn" else T)
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(W, wl.tokens_per_window, wl.d_model, generator=g).abs_()
+    labs = None
+    if wl.kind == "ltn":
+        pseudo = (torch.rand(B, P * T, generator=g) > 0.9).float() * torch.rand(B, P * T, generator=g)
+        labs = losses.soft_clip_labels(pseudo, B, P, T)
+    if pin:
+        feats = feats.pin_memory()
+        labs = labs.pin_memory() if labs is not None else None
+    if device != "cpu":
+        feats = feats.to(device, non_blocking=True)
+        labs = labs.to(device, non_blocking=True) if labs is not None else None
+    return feats, labs
+
+
+# --------------------------------------------------------------------------------------------------
+# single-GPU / per-rank train step
+# --------------------------------------------------------------------------------------------------
+class TrainStep:
+    """Forward + loss + backward of one reference train step on this rank's share of the batch.
+
+    With `world_size > 1` the batch is sharded by VIDEO PAIR (all P windows of a bag stay on one rank); the
+    MIL hinge couples bags across ranks, so the per-window scores (a few KB) are all-gathered and every rank
+    evaluates the global MIL loss and keeps the gradient slice of its own windows; CE is a share of the global
+    mean.  Parameter gradients are then SUM-all-reduced in buckets, overlapped with the rest of backward."""
+
+    def __init__(self, wl: Workload, device: torch.device, seed: int = 0, train_mode: bool = True,
+                 lambda_1: float = 0.01, lambda_MIL: float = 1.0, lambda_CE: float = 0.8,
+                 process_group=None, optimizer: bool = False, lr_encoder: float = 1e-4, lr_head: float = 1e-2,
+                 weight_decay: float = 1e-3):
+        self.wl, self.device = wl, device
+        self.lambda_1, self.lambda_MIL, self.lambda_CE = lambda_1, lambda_MIL, lambda_CE
+        self.pg = process_group
+        self.world = 1
+        self.rank = 0
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        torch.manual_seed(seed)  # identical initial weights on every rank
+        self.encoder = Encoder(**wl.encoder_kwargs()).to(device)
+        head_drop = wl.dropouts[3]
+        self.head = (Classifier(wl.d_model, head_drop) if wl.kind == "ltn" else Regressor(wl.d_model, head_drop)).to(device)
+        self.encoder.train(train_mode)
+        self.head.train(train_mode)
+        Fn.set_dropout_stream(seed * 1000003 + 7919 * self.rank + 1)
+        self.reducer = None
+        if self.world > 1:
+            self.reducer = BucketedGradReducer([self.encoder, self.head], process_group)
+        self.opt = None
+        if optimizer:
+            self.opt = FusedAdagrad([(list(self.encoder.parameters()), lr_encoder),
+                                     (list(self.head.parameters()), lr_head)], weight_decay)
+
+    def parameters(self):
+        return list(self.encoder.parameters()) + list(self.head.parameters())
+
+    def zero_grad(self):
+        for p in self.parameters():
+            p.grad = None
+
+    def forward_backward(self, feats: torch.Tensor, labs: Optional[torch.Tensor], local_batch: int) -> Dict[str, torch.Tensor]:
+        """feats [W_local, L0, D] on device (normal windows of this rank's bags first, then abnormal);
+        labs [W_local, 2].  Returns the (global) loss terms as device scalars."""
+        wl = self.wl
+        B, P, T = local_batch, wl.part_num, wl.part_len
+        args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=T, lambda_1=self.lambda_1)
+        if self.reducer is not None:
+            self.reducer.start()
+        out = self.encoder(feats)
+        cls_rows = out[:, 0, :]
+        if wl.kind == "ltn":
+            probs = self.head(cls_rows.view(2 * B, P, wl.d_model)).view(2 * B * P, -1)
+            score = probs[:, 1]
+            if self.world == 1:
+                ce = losses.get_CE_loss(args, probs, labs)
+                mil, err, l1 = losses.get_MIL_loss(args, score)
+            else:
+                ce = losses.get_CE_loss(args, probs, labs) / self.world
+                mil, err, l1 = self._global_mil(score, B, P, 1, flat=True)
+            loss = self.lambda_MIL * mil + self.lambda_CE * ce
+            terms = dict(loss=loss, mil=mil, ce=ce, err=err, spar=l1, scores=score)
+        else:
+            score = self.head(cls_rows.view(2 * B, P * T, wl.d_model)).view(2 * B, P * T, 1)
+            if self.world == 1:
+                mil, err, l1 = losses.get_MIL_loss(args, score)
+            else:
+                mil, err, l1 = self._global_mil(score, B, P, T, flat=False)
+            loss = mil
+            terms = dict(loss=loss, mil=mil, err=err, spar=l1, scores=score)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        if self.opt is not None:
+            self.opt.step()
+        return terms
+
+    # -- MIL across ranks: all-gather the scores, evaluate the global loss everywhere, keep the local slice --
+    def _global_mil(self, score: torch.Tensor, B: int, P: int, T: int, flat: bool):
+        import torch.distributed as dist
+        n_local = score.numel()
+        half = n_local // 2
+        flat_local = score.reshape(-1).contiguous()
+        gathered = [torch.empty_like(flat_local) for _ in range(self.world)]
+        dist.all_gather(gathered, flat_local.detach(), group=self.pg)
+        # reference order: all normal bags (rank-major), then all abnormal bags
+        glob = torch.cat([g[:half] for g in gathered] + [g[half:] for g in gathered])
+        Bg = B * self.world
+        spar_start = Bg if flat else Bg * P * T
+        out3, _, dglob = ops.mil_loss(glob, Bg, P, T, 1, self.lambda_1, spar_start)
+        d_local = torch.cat([dglob[self.rank * half:(self.rank + 1) * half],
+                             dglob[Bg * P * T + self.rank * half: Bg * P * T + (self.rank + 1) * half]])
+        mil = _InjectGrad.apply(flat_local, out3[0], d_local)
+        return mil, out3[1], out3[2]
+
+
+class _InjectGrad(torch.autograd.Function):
+    """value (precomputed global loss) whose gradient w.r.t. `scores` is the given slice."""
+
+    @staticmethod
+    def forward(ctx, scores, value, dscores):
+        ctx.save_for_backward(dscores)
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return ops.scale_by_device_scalar(d, g.reshape(1).contiguous()), None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# bucketed gradient all-reduce overlapped with backward (replaces nn.DataParallel's reduce_add_coalesced,
+# Train/temporal_transformer_shanghaitech.py:76-78)
+# --------------------------------------------------------------------------------------------------
+class BucketedGradReducer:
+    """One bucket per EncoderLayer (+ one for everything else), reduced in reverse layer order as soon as the
+    last gradient of the bucket has been accumulated.  The bucket plan is static and only contains parameters
+    that receive gradients (LayerNorms switched off by the model flags never do — SURVEY.md §8)."""
+
+    def __init__(self, modules: Sequence[torch.nn.Module], process_group, comm_stream: Optional[torch.cuda.Stream] = None):
+        import torch.distributed as dist
+        self.dist, self.pg = dist, process_group
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        self._plan(modules)
+        self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self.pending: List[int] = [0] * len(self.buckets)
+        self.handles = []
+        self.stream = comm_stream or torch.cuda.Stream()
+        self._active = False
+        self._skip: set = set()
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                p.register_post_accumulate_grad_hook(self._make_hook(bi))
+
+    def _plan(self, modules):
+        rest = []
+        for m in modules:
+            stack = getattr(m, "layer_stack", None)
+            in_layers = set()
+            if stack is not None:
+                for layer in stack:
+                    ps = [p for p in layer.parameters() if p.requires_grad]
+                    in_layers.update(id(p) for p in ps)
+                    self.buckets.append(ps)
+            rest += [p for p in m.parameters() if p.requires_grad and id(p) not in in_layers]
+        if rest:
+            self.buckets.append(rest)
+
+    def mark_unused(self, params):
+        """Parameters that never receive a gradient (found by a warm-up step) are dropped from the plan."""
+        self._skip.update(id(p) for p in params)
+
+    def _make_hook(self, bi):
+        def hook(p):
+            if not self._active:
+                return
+            self.pending[bi] -= 1
+            if self.pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def start(self):
+        self._active = True
+        self.handles = []
+        for bi, bucket in enumerate(self.buckets):
+            self.pending[bi] = sum(1 for p in bucket if id(p) not in self._skip)
+
+    def _launch(self, bi):
+        ps = [p for p in self.buckets[bi] if id(p) not in self._skip and p.grad is not None]
+        if not ps:
+            return
+        n = sum(p.numel() for p in ps)
+        if self.flat[bi] is None or self.flat[bi].numel() != n:
+            self.flat[bi] = torch.empty(n, device=ps[0].device, dtype=torch.float32)
+        flat = self.flat[bi]
+        views, off = [], 0
+        for p in ps:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        torch._foreach_copy_(views, [p.grad for p in ps])
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.pg)
+        for p, v in zip(ps, views):
+            p.grad = v  # the optimizer reads the reduced bucket in place
+        self.handles.append(bi)
+
+    def finish(self):
+        # buckets whose parameters did not all fire (unused params): flush them now
+        for bi in range(len(self.buckets)):
+            if self.pending[bi] > 0:
+                unused = [p for p in self.buckets[bi] if p.grad is None]
+                self.mark_unused(unused)
+                self.pending[bi] = 0
+                self._launch(bi)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self._active = False
+
+
+class FusedAdagrad:
+    """torch.optim.Adagrad(lr per group, weight_decay) semantics (Train/temporal_transformer_shanghaitech.py:83-85)
+    with one fused kernel per parameter: 5 HBM passes (read grad/param/state, write param/state)."""
+
+    def __init__(self, groups, weight_decay: float, eps: float = 1e-10):
+        self.groups = groups
+        self.wd, self.eps = weight_decay, eps
+        self.state: Dict[int, torch.Tensor] = {}
+
+    def step(self):
+        for params, lr in self.groups:
+            for p in params:
+                if p.grad is None:
+                    continue
+                st = self.state.get(id(p))
+                if st is None:
+                    st = self.state[id(p)] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ops.adagrad_step(p.data, p.grad.contiguous(), st, lr, self.wd, self.eps)
+        Fn.invalidate_weight_cache()  # parameters were updated through raw pointers
+
+
+# --------------------------------------------------------------------------------------------------
+# batched, sharded scoring / pseudo-label generation (no collective)
+# --------------------------------------------------------------------------------------------------
+def video_windows(n_clips: int, part_len: int, backshift: bool) -> List[Tuple[int, int, int]]:
+    """(feat_beg, feat_end, n_clips_covered) per window.  backshift=False: short trailing window
+    (Train/pseudo_labels_generator_temporal.py:127-134); True: trailing window moved back to full length while
+    its score still covers only the remaining clips (Test/evaluation_shanghaitech_ubnormal.py:74-92)."""
+    out = []
+    n_win = (n_clips + part_len - 1) // part_len
+    for i in range(n_win):
+        beg = i * part_len
+        end = n_clips if i == n_win - 1 else (i + 1) * part_len
+        if backshift and end - beg < part_len and end - part_len >= 0:
+            out.append((end - part_len, end, end - beg))
+        else:
+            out.append((beg, end, end - beg))
+    return out
+
+
+def shard_videos(keys: Sequence[str], n_clips: Sequence[int], world: int, rank: int) -> List[int]:
+    """Greedy longest-first assignment of videos to ranks (balanced by clip count); returns this rank's indices."""
+    order = sorted(range(len(keys)), key=lambda i: (-n_clips[i], keys[i]))
+    load = [0] * world
+    mine = []
+    for i in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        load[r] += n_clips[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+@torch.no_grad()
+def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torch.Tensor], part_len: int,
+                 backshift: bool = False, threshold: Optional[float] = None, max_windows: int = 4096,
+                 n_patch: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """Per-clip scores for every video of this rank's shard: {key: fp32 [n_clips]} on the CPU.
+
+    Windows of equal token count from ALL videos are batched into a few large forward calls instead of the
+    reference's one-window-per-forward loop; `threshold` applies where(score > thr, score, 0)."""
+    encoder.eval()
+    head.eval()
+    dev = next(encoder.parameters()).device
+    groups: Dict[int, List[Tuple[str, int, int, int, int]]] = {}
+    for key, feats in videos.items():
+        n = feats.shape[0]
+        for wi, (b, e, cover) in enumerate(video_windows(n, part_len, backshift)):
+            groups.setdefault(e - b, []).append((key, wi, b, e, cover))
+    win_scores: Dict[Tuple[str, int], float] = {}
+    is_cls = isinstance(head, Classifier)
+    for n_clip_win, items in groups.items():
+        for s in range(0, len(items), max_windows):
+            chunk = items[s:s + max_windows]
+            batch = torch.stack([videos[k][b:e, :n_patch].reshape(-1, videos[k].shape[-1]) for k, _, b, e, _ in chunk])
+            out = encoder(batch.to(dev, non_blocking=True).float())
+            sc = head(out[:, 0, :])
+            sc = sc[:, 1] if is_cls else sc[:, 0]
+            if threshold is not None:
+                sc = losses.threshold_pseudo_labels(sc, threshold)
+            sc = sc.cpu()
+            for (k, wi, _, _, _), v in zip(chunk, sc.tolist()):
+                win_scores[(k, wi)] = v
+    result = {}
+    for key, feats in videos.items():
+        vals = []
+        for wi, (_, _, cover) in enumerate(video_windows(feats.shape[0], part_len, backshift)):
+            vals += [win_scores[(key, wi)]] * cover
+        result[key] = torch.tensor(vals, dtype=torch.float32)
+    return result

@@ -19,6 +19,44 @@ Dropout = Tuple[float, int, int]  # (p, seed, offset)
 NO_DROPOUT: Dropout = (0.0, 0, 0)
 
 
+class _LaunchCounter:
+    """Counts kernel launches issued through this module (bench.py reports it as `gpu_launches`)."""
+
+    def __init__(self):
+        self.count = 0
+
+    def reset(self):
+        self.count = 0
+
+    def add(self, n: int = 1):
+        self.count += n
+
+
+class _GemmProfiler:
+    """Optional CUDA-event bracket around every GEMM launch (on the launching stream) — used by bench.py to
+    measure the tensor-core kernel live inside the timed region."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def enable(self):
+        self.enabled, self.records = True, []
+
+    def disable(self):
+        self.enabled = False
+
+    def collect(self):
+        torch.cuda.synchronize()
+        out = [dict(kind=k, flops=f, ms=e0.elapsed_time(e1), shape=shape) for k, f, shape, e0, e1 in self.records]
+        self.records = []
+        return out
+
+
+LAUNCHES = _LaunchCounter()
+PROFILE = _GemmProfiler()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -80,10 +118,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         _cuda(residual, "residual", BF16)
         ld_res = _rowmajor2d(residual, "residual")
     p, seed, off = dropout
+    prof = PROFILE.enabled
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     st = lib.lstc_gemm_bf16(_p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), M, N, K, _p(out), ldc,
                             int(out.dtype == F32), _p(bias), int(relu), _p(relu_mask), ld_mask, _p(residual), ld_res,
                             float(p), int(seed), int(off), int(split_k), int(accumulate), _stream())
+    if prof:
+        e1.record()
+        kind = ("mn" if a_mn else "k") + "-" + ("mn" if b_mn else "k")
+        PROFILE.records.append((kind, 2.0 * M * N * K, (M, N, K), e0, e1))
     _lib.check(st, "lstc_gemm_bf16")
+    LAUNCHES.add(1)
     return out
 
 
@@ -99,6 +146,7 @@ def relbias_gather(table: torch.Tensor, index: torch.Tensor, L: int) -> torch.Te
     dense = torch.empty((H, L, L), device=table.device, dtype=F32)
     st = lib.lstc_relbias_gather(_p(table), _p(index), index.shape[-1], L, H, T, _p(dense), _stream())
     _lib.check(st, "lstc_relbias_gather")
+    LAUNCHES.add(1)
     return dense
 
 
@@ -111,6 +159,7 @@ def relbias_scatter(ddense: torch.Tensor, index: torch.Tensor, T: int) -> torch.
     dtable = torch.empty((T, H), device=ddense.device, dtype=F32)
     st = lib.lstc_relbias_scatter(_p(ddense.contiguous()), _p(index), index.shape[-1], L, H, T, _p(dtable), _stream())
     _lib.check(st, "lstc_relbias_scatter")
+    LAUNCHES.add(1)
     return dtable
 
 
@@ -132,6 +181,7 @@ def attn_fwd(qkv: torch.Tensor, W: int, L: int, H: int, dk: int, bias: Optional[
     st = lib.lstc_attn_fwd(_p(qkv), ld, W, L, H, dk, _p(bias), float(scale), float(p), int(seed), int(off), _p(out),
                            H * dk, _p(probs), _stream())
     _lib.check(st, "lstc_attn_fwd")
+    LAUNCHES.add(1)
     return out, probs
 
 
@@ -150,6 +200,7 @@ def attn_bwd(qkv: torch.Tensor, dout: torch.Tensor, W: int, L: int, H: int, dk: 
     st = lib.lstc_attn_bwd(_p(qkv), ld, _p(dout), ldo, W, L, H, dk, _p(bias), float(scale), float(p), int(seed),
                            int(off), _p(dqkv), 3 * H * dk, _p(dbias), _stream())
     _lib.check(st, "lstc_attn_bwd")
+    LAUNCHES.add(1)
     return dqkv, dbias
 
 
@@ -170,6 +221,7 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     st = lib.lstc_layernorm_fwd(_p(x), int(x.dtype == F32), _p(gamma), _p(beta), _p(y), int(out_dtype == F32),
                                 _p(mean), _p(rstd), rows, D, float(eps), _stream())
     _lib.check(st, "lstc_layernorm_fwd")
+    LAUNCHES.add(1)
     return y, mean, rstd
 
 
@@ -193,6 +245,7 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
                                 _p(rstd), _p(dx), int(dx.dtype == F32), _p(dx_drop), float(p), int(seed), int(off),
                                 _p(dgamma), _p(dbeta), _p(ws), rows, D, _stream())
     _lib.check(st, "lstc_layernorm_bwd")
+    LAUNCHES.add(2)
     return dx, dx_drop, dgamma, dbeta
 
 
@@ -219,6 +272,7 @@ def cls_prepend_fwd(x: torch.Tensor, cls: Optional[torch.Tensor] = None, pos: Op
     st = lib.lstc_cls_prepend_fwd(_p(x), int(x.dtype == F32), _p(cls), _p(pos), float(p), int(seed), int(off),
                                   _p(out), W, L0, D, _stream())
     _lib.check(st, "lstc_cls_prepend_fwd")
+    LAUNCHES.add(1)
     return out
 
 
@@ -237,6 +291,7 @@ def cls_prepend_bwd(g: torch.Tensor, cls_learned: bool, need_dx: bool, need_dpos
     st = lib.lstc_cls_prepend_bwd(_p(g), int(cls_learned), float(p), int(seed), int(off), _p(dx), _p(dcls), _p(dpos),
                                   W, L0, D, _stream())
     _lib.check(st, "lstc_cls_prepend_bwd")
+    LAUNCHES.add(1)
     return dx, dcls, dpos
 
 
@@ -258,6 +313,7 @@ def head_tail_fwd(h1: torch.Tensor, W2, b2, W3, b3, sigmoid: bool, dropout: Drop
                                 _p(b3.contiguous()), C, int(sigmoid), float(p), int(seed), int(off), _p(h2), _p(out),
                                 _stream())
     _lib.check(st, "lstc_head_tail_fwd")
+    LAUNCHES.add(1)
     return h2, out
 
 
@@ -278,6 +334,7 @@ def head_tail_bwd(dout: torch.Tensor, out: torch.Tensor, h2: torch.Tensor, W3: t
     st = lib.lstc_head_tail_bwd(_p(dout), _p(out), _p(h2), _p(W3.contiguous()), n, C, int(sigmoid), float(p),
                                 int(seed), int(off), _p(dh2), _p(dW3), _p(db3), _stream())
     _lib.check(st, "lstc_head_tail_bwd")
+    LAUNCHES.add(1)
     return dh2, dW3, db3
 
 
@@ -306,6 +363,7 @@ def mil_loss(scores: torch.Tensor, B: int, P: int, T: int = 1, topk: int = 1, la
     st = lib.lstc_mil_loss(_p(flat), 1, B, P, T, topk, float(lambda1), int(spar_start), _p(out3), _p(top_idx),
                            _p(dscores), _stream())
     _lib.check(st, "lstc_mil_loss")
+    LAUNCHES.add(1)
     return out3, top_idx, dscores
 
 
@@ -321,6 +379,7 @@ def soft_ce_loss(probs: torch.Tensor, labels: torch.Tensor, need_grad: bool = Tr
     dprobs = torch.empty_like(probs) if need_grad else None
     st = lib.lstc_soft_ce_loss(_p(probs), _p(labels), n, C, _p(out1), _p(dprobs), _stream())
     _lib.check(st, "lstc_soft_ce_loss")
+    LAUNCHES.add(1)
     return out1, dprobs
 
 
@@ -339,6 +398,7 @@ def bce_loss(scores: torch.Tensor, labels: torch.Tensor, T: int, w_normal: float
     st = lib.lstc_bce_loss(_p(scores), _p(labels), n_parts, T, float(w_normal), float(w_abnormal), _p(out1),
                            _p(dscores), _stream())
     _lib.check(st, "lstc_bce_loss")
+    LAUNCHES.add(1)
     return out1, dscores
 
 
@@ -349,6 +409,7 @@ def threshold_labels(scores: torch.Tensor, thr: float) -> torch.Tensor:
     out = torch.empty_like(scores)
     st = lib.lstc_threshold_labels(_p(scores), float(thr), _p(out), scores.numel(), _stream())
     _lib.check(st, "lstc_threshold_labels")
+    LAUNCHES.add(1)
     return out
 
 
@@ -361,6 +422,7 @@ def cast_to_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
         out = torch.empty(x.shape, device=x.device, dtype=BF16)
     st = lib.lstc_cast_f32_to_bf16(_p(x), _p(out), x.numel(), _stream())
     _lib.check(st, "lstc_cast_f32_to_bf16")
+    LAUNCHES.add(1)
     return out
 
 
@@ -371,6 +433,7 @@ def cast_to_f32(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape, device=x.device, dtype=F32)
     st = lib.lstc_cast_bf16_to_f32(_p(x), _p(out), x.numel(), _stream())
     _lib.check(st, "lstc_cast_bf16_to_f32")
+    LAUNCHES.add(1)
     return out
 
 
@@ -384,6 +447,7 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     ws = torch.empty(max(1, lib.lstc_colsum_workspace(rows, cols)), device=x.device, dtype=torch.uint8)
     st = lib.lstc_colsum_bf16(_p(x), rows, cols, ld, _p(out), _p(ws), _stream())
     _lib.check(st, "lstc_colsum_bf16")
+    LAUNCHES.add(2)
     return out
 
 
@@ -397,6 +461,7 @@ def dropout_apply(x: torch.Tensor, dropout: Dropout) -> torch.Tensor:
     p, seed, off = dropout
     st = lib.lstc_dropout_apply_bf16(_p(x), _p(y), rows, cols, float(p), int(seed), int(off), _stream())
     _lib.check(st, "lstc_dropout_apply_bf16")
+    LAUNCHES.add(1)
     return y
 
 
@@ -408,6 +473,7 @@ def dropout_mask(rows: int, cols: int, dropout: Dropout, device=None) -> torch.T
     p, seed, off = dropout
     st = lib.lstc_dropout_mask(_p(mask), rows, cols, float(p), int(seed), int(off), _stream())
     _lib.check(st, "lstc_dropout_mask")
+    LAUNCHES.add(1)
     return mask
 
 
@@ -419,6 +485,7 @@ def scale_by_device_scalar(src: torch.Tensor, scalar: torch.Tensor) -> torch.Ten
     dst = torch.empty_like(src)
     st = lib.lstc_scale_by_device_scalar(_p(src), _p(scalar), _p(dst), src.numel(), _stream())
     _lib.check(st, "lstc_scale_by_device_scalar")
+    LAUNCHES.add(1)
     return dst
 
 
@@ -432,3 +499,4 @@ def adagrad_step(param: torch.Tensor, grad: torch.Tensor, state_sum: torch.Tenso
     st = lib.lstc_adagrad_step(_p(param), _p(grad), _p(state_sum), param.numel(), float(lr), float(weight_decay),
                                float(eps), float(grad_scale), _stream())
     _lib.check(st, "lstc_adagrad_step")
+    LAUNCHES.add(1)

@@ -1,0 +1,286 @@
+"""Module-level parity (GPU): the lstc_vad_b200.models mirror against
+  (a) golden vectors computed by the unmodified reference (tests/golden/, small configs), and
+  (b) the CPU oracle on the same seeded inputs at the shipped shapes (d_model 2048 / 1024).
+
+Stated tolerances (bf16 operands, fp32 accumulate; the reference itself moves by 1.6e-3 on scores between
+fp32 and bf16 autocast):
+  encoder output   max-abs <= 4e-2 * max|ref|      scores / probabilities   max-abs <= 5e-3
+  losses           abs <= 5e-3                      gradients  max-abs <= 6e-2 * max|ref grad| per tensor
+  top-k indices / thresholded labels: bit-exact whenever the selected scores are separated by > 1e-2.
+"""
+import types
+from pathlib import Path
+
+import pytest
+import torch
+
+from tests._util import report
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def rel_close(name, got, ref, rel, floor=1e-6):
+    scale = max(ref.detach().abs().max().item(), floor)
+    ok, msg = report(name, got, ref, 0.0, rel * scale)
+    assert ok, msg
+
+
+def abs_close(name, got, ref, atol):
+    ok, msg = report(name, got, ref, 0.0, atol)
+    assert ok, msg
+
+
+def load(name):
+    return torch.load(GOLD / f"{name}.pt", weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def M():
+    import lstc_vad_b200.models as models
+    return models
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lstc_vad_b200.losses as losses
+    return losses
+
+
+@pytest.mark.parametrize("name", ["ltn_relpe", "ltn_ucf_sliced"])
+def test_ltn_against_reference_golden(M, L, name):
+    c = load(name)
+    enc = M.Encoder(**c["enc_kwargs"])
+    cls = M.Classifier(c["enc_kwargs"]["d_model"], 0.6)
+    # strict load proves key-for-key / shape-for-shape state_dict compatibility with reference checkpoints
+    enc.load_state_dict(c["enc_state"], strict=True)
+    cls.load_state_dict(c["cls_state"], strict=True)
+    enc, cls = enc.cuda().eval(), cls.cuda().eval()
+    B, P, D = c["B"], c["P"], c["enc_kwargs"]["d_model"]
+    x = c["x"].cuda().requires_grad_(True)
+    out, attn_list, v_list = enc(x, return_attn_v=True)
+    assert out.dtype == torch.float32 and tuple(out.shape) == tuple(c["enc_out"].shape)
+    rel_close(f"{name} enc_out", out, c["enc_out"], 4e-2)
+    abs_close(f"{name} attn0", attn_list[0], c["attn0"], 5e-3)
+    rel_close(f"{name} v0", v_list[0], c["v0"], 2e-2)
+    # the loop body of Train/temporal_transformer_shanghaitech.py:122-134 on the mirror
+    args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=c["T"], lambda_1=0.01)
+    feats = out[:, 0, :].float().view([2 * B, P, D])
+    outputs = cls(feats).view([2 * B * P, -1])
+    abs_close(f"{name} probs", outputs, c["probs"], 5e-3)
+    labs = L.soft_clip_labels(c["clip_pseudo"].cuda(), B, P, c["T"])
+    abs_close("soft labels", labs, c["clip_labs"], 1e-6)
+    ce = L.get_CE_loss(args, outputs, labs)
+    mil, err, l1 = L.get_MIL_loss(args, outputs[:, 1])
+    loss = 1.0 * mil + 0.8 * ce
+    for nm, got in (("ce", ce), ("mil", mil), ("err", err), ("spar", l1), ("loss", loss)):
+        abs_close(f"{name} {nm}", got.reshape(1), c[nm].reshape(1), 5e-3)
+    loss.backward()
+    rel_close(f"{name} x.grad", x.grad, c["x_grad"], 6e-2)
+    for k, g in c["enc_grads"].items():
+        p = dict(enc.named_parameters())[k]
+        if g is None:
+            assert p.grad is None, f"{k} should not receive a gradient"
+        else:
+            assert p.grad is not None, f"{k} got no gradient"
+            rel_close(f"{name} grad {k}", p.grad, g, 6e-2)
+    for k, g in c["cls_grads"].items():
+        rel_close(f"{name} cls grad {k}", dict(cls.named_parameters())[k].grad, g, 6e-2)
+    # top-k indices: exact wherever the reference bag maximum is separated from the runner-up
+    idx = L.mil_topk_indices(args, outputs[:, 1])[:, 0].cpu()
+    ref_scores = c["probs"][:, 1].view(2 * B, P)
+    top2 = ref_scores.topk(min(2, P), dim=-1).values
+    sep = (top2[:, 0] - top2[:, -1]) > 1e-2 if P > 1 else torch.ones(2 * B, dtype=torch.bool)
+    assert torch.equal(idx[sep].long(), c["topk_idx"][sep])
+    # variable-length windows (short trailing windows of the labelling loop)
+    with torch.no_grad():
+        for L0, v in c["var_L"].items():
+            o = enc(v["x"].cuda())
+            rel_close(f"{name} var L0={L0} enc_out", o, v["enc_out"], 4e-2)
+            abs_close(f"{name} var L0={L0} probs", cls(o[:, 0, :]), v["probs"], 5e-3)
+
+
+@pytest.mark.parametrize("name", ["stn_plain", "stn_relpe2d_cls_pos"])
+def test_stn_against_reference_golden(M, L, name):
+    c = load(name)
+    D = c["enc_kwargs"]["d_model"]
+    enc = M.Encoder(**c["enc_kwargs"])
+    reg = M.Regressor(D, 0.6)
+    enc.load_state_dict(c["enc_state"], strict=True)
+    reg.load_state_dict(c["reg_state"], strict=True)
+    enc, reg = enc.cuda().eval(), reg.cuda().eval()
+    B, P, T = c["B"], c["P"], c["T"]
+    x = c["x"].cuda().requires_grad_(True)
+    out = enc(x)
+    rel_close(f"{name} enc_out", out, c["enc_out"], 4e-2)
+    args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=T, lambda_1=0.01, lambda_normal=0.2,
+                                 lambda_abnormal=2.0)
+    feats = out[:, 0, :].float().view([2 * B, P * T, D])
+    outputs = reg(feats).view([2 * B, P * T, 1])
+    abs_close(f"{name} scores", outputs, c["scores"], 5e-3)
+    mil, err, l1 = L.get_MIL_loss(args, outputs)
+    part = torch.mean(outputs.view([2 * B, P, T]), dim=-1)
+    bce = L.get_BCE_loss(args, part, c["bce_labs"].cuda())
+    loss = mil + 0.5 * bce
+    for nm, got in (("mil", mil), ("err", err), ("spar", l1), ("bce", bce), ("loss", loss)):
+        abs_close(f"{name} {nm}", got.reshape(1), c[nm].reshape(1), 5e-3)
+    loss.backward()
+    rel_close(f"{name} x.grad", x.grad, c["x_grad"], 6e-2)
+    for k, g in c["enc_grads"].items():
+        p = dict(enc.named_parameters())[k]
+        if g is None:
+            assert p.grad is None, f"{k} should not receive a gradient"
+        else:
+            rel_close(f"{name} grad {k}", p.grad, g, 6e-2)
+    for k, g in c["reg_grads"].items():
+        rel_close(f"{name} reg grad {k}", dict(reg.named_parameters())[k].grad, g, 6e-2)
+
+
+# ------------------------------------------------------------------------------------------------------
+# shipped shapes vs the CPU oracle (same seeded inputs; sizes the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------------------
+SHAPES = {
+    # name: (enc kwargs, B, P, T, N)
+    "C2_ltn_sht": (dict(n_layers=3, n_head=8, d_k=256, d_v=256, d_model=2048, d_inner=4096, MHA_layerNorm=True,
+                        FFN_layerNorm=True, weight_init=False, relative_pe=True, window_size=4, window_depth=3),
+                   2, 4, 3, 16),
+    "C3_ltn_ucf": (dict(n_layers=3, n_head=8, d_k=256, d_v=256, d_model=2048, d_inner=4096, MHA_layerNorm=True,
+                        FFN_layerNorm=True, weight_init=False, relative_pe=True, window_size=4, window_depth=2),
+                   2, 4, 2, 9),
+    "C4_ltn_ubnormal": (dict(n_layers=3, n_head=8, d_k=256, d_v=256, d_model=1024, d_inner=4096, MHA_layerNorm=True,
+                             FFN_layerNorm=True, weight_init=False, relative_pe=True, window_size=4, window_depth=5),
+                        2, 3, 5, 16),
+}
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_ltn_full_width_against_oracle(M, L, name):
+    from oracle import lstc_oracle as O
+    kw, B, P, T, N = SHAPES[name]
+    D = kw["d_model"]
+    torch.manual_seed(0)
+    enc = M.Encoder(**kw)
+    cls = M.Classifier(D, 0.6, weight_init=True)
+    enc_sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    cls_sd = {k: v.clone() for k, v in cls.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2 * B * P, T * N, D, generator=g).abs()
+    pseudo = (torch.rand(B, P * T, generator=g) > 0.9).float()
+    labs = O.soft_labels(pseudo, B, P, T)
+    # oracle (CPU fp32) with gradients
+    cfg = O.EncoderConfig(**{k: v for k, v in kw.items() if k in O.EncoderConfig.__dataclass_fields__})
+    esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in enc_sd.items()}
+    csd = {k: v.clone().requires_grad_(True) for k, v in cls_sd.items()}
+    xo = x.clone().requires_grad_(True)
+    ref_loss, aux = O.ltn_train_loss(esd, csd, xo, labs, cfg, B, P)
+    ref_loss.backward()
+    # CUDA path
+    enc, cls = enc.cuda().eval(), cls.cuda().eval()
+    args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=T, lambda_1=0.01)
+    xc = x.cuda().requires_grad_(True)
+    out = enc(xc)
+    probs = cls(out[:, 0, :].float().view([2 * B, P, D])).view(2 * B * P, -1)
+    abs_close(f"{name} probs", probs, aux["probs"], 5e-3)
+    ce = L.get_CE_loss(args, probs, labs.cuda())
+    mil, err, l1 = L.get_MIL_loss(args, probs[:, 1])
+    loss = mil + 0.8 * ce
+    abs_close(f"{name} loss", loss.reshape(1), ref_loss.detach().reshape(1), 5e-3)
+    loss.backward()
+    rel_close(f"{name} x.grad", xc.grad, xo.grad, 6e-2)
+    params = dict(enc.named_parameters())
+    for k in ("layer_stack.0.slf_attn.w_qs.weight", "layer_stack.0.slf_attn.relative_position_bias_table",
+              "layer_stack.1.slf_attn.fc.weight", "layer_stack.1.pos_ffn.w_1.weight", "layer_stack.1.pos_ffn.w_1.bias",
+              "layer_stack.2.pos_ffn.w_2.weight", "layer_stack.2.pos_ffn.w_2.bias",
+              "layer_stack.2.slf_attn.layer_norm.weight", "layer_stack.0.pos_ffn.layer_norm.bias"):
+        rel_close(f"{name} grad {k}", params[k].grad, esd[k].grad, 6e-2)
+    for k, p in cls.named_parameters():
+        rel_close(f"{name} cls grad {k}", p.grad, csd[k].grad, 6e-2)
+
+
+def test_stn_odd_hidden_width_3027(M):
+    """STN default n_hidden 3027 (Train/spatio_transformer_shanghaitech.py:216): not a multiple of 8, handled by
+    zero-padding the cached bf16 weights; state_dict keeps [3027,2048] / [2048,3027]."""
+    from oracle import lstc_oracle as O
+    kw = dict(n_layers=1, n_head=8, d_k=256, d_v=256, d_model=2048, d_inner=3027, MHA_layerNorm=False,
+              FFN_layerNorm=True, weight_init=True)
+    torch.manual_seed(3)
+    enc = M.Encoder(**kw)
+    assert tuple(enc.state_dict()["layer_stack.0.pos_ffn.w_1.weight"].shape) == (3027, 2048)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    x = torch.randn(6, 16, 2048, generator=torch.Generator().manual_seed(4)).abs()
+    cfg = O.EncoderConfig(**{k: v for k, v in kw.items() if k in O.EncoderConfig.__dataclass_fields__})
+    ref = O.encoder_forward(sd, x, cfg)
+    gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    ref.backward(gout)
+    enc = enc.cuda().train()  # all dropout p default 0.1 -> use eval for determinism
+    enc.eval()
+    out = enc(x.cuda())
+    rel_close("stn3027 enc_out", out, ref, 4e-2)
+    out.backward(gout.cuda())
+    p = dict(enc.named_parameters())
+    for k in ("layer_stack.0.pos_ffn.w_1.weight", "layer_stack.0.pos_ffn.w_2.weight", "layer_stack.0.pos_ffn.w_1.bias",
+              "layer_stack.0.slf_attn.fc.weight"):
+        assert p[k].grad.shape == p[k].shape
+        rel_close(f"stn3027 grad {k}", p[k].grad, sd[k].grad, 6e-2)
+
+
+def test_train_mode_dropout_replay_against_oracle(M):
+    """Train mode: dump the exact Philox masks the kernels used and replay them through the oracle."""
+    from oracle import lstc_oracle as O
+    from lstc_vad_b200 import ops, set_dropout_stream
+    kw = dict(n_layers=2, n_head=2, d_k=64, d_v=64, d_model=128, d_inner=256, MHA_layerNorm=True, FFN_layerNorm=True,
+              weight_init=False, relative_pe=True, window_size=4, window_depth=3, MHA_attn_dropout=0.2,
+              MHA_fc_dropout=0.2, FFN_dropout=0.1)
+    torch.manual_seed(7)
+    enc = M.Encoder(**kw)
+    sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    W, L0, D, H = 5, 48, 128, 2
+    Lt = L0 + 1
+    x = torch.randn(W, L0, D, generator=torch.Generator().manual_seed(8)).abs()
+    enc = enc.cuda().train()
+    seed = 12345
+    set_dropout_stream(seed, 0)
+    out = enc(x.cuda())
+    # offsets are consumed in call order: per layer attn (1), fc (2), ffn (3), then 4, 5, 6
+    masks = O.DropoutMasks(attn_p=0.2, fc_p=0.2, ffn_p=0.1)
+    off = 0
+    for i in range(2):
+        masks.attn[i] = ops.dropout_mask(W * H * Lt, Lt, (0.2, seed, off + 1)).view(W, H, Lt, Lt).cpu().float()
+        masks.fc[i] = ops.dropout_mask(W * Lt, D, (0.2, seed, off + 2)).view(W, Lt, D).cpu().float()
+        masks.ffn[i] = ops.dropout_mask(W * Lt, D, (0.1, seed, off + 3)).view(W, Lt, D).cpu().float()
+        off += 3
+    cfg = O.EncoderConfig(**{k: v for k, v in kw.items() if k in O.EncoderConfig.__dataclass_fields__})
+    ref = O.encoder_forward(sd, x, cfg, masks)
+    rel_close("dropout replay enc_out", out, ref, 4e-2)
+    # and the masks really are ~Bernoulli(1-p)
+    assert abs(masks.attn[0].mean().item() - 0.8) < 0.02 and abs(masks.ffn[1].mean().item() - 0.9) < 0.02
+
+
+def test_modules_reject_cpu_tensors_and_masks(M):
+    enc = M.Encoder(n_layers=1, n_head=1, d_k=64, d_v=64, d_model=64, d_inner=64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.zeros(1, 4, 64))
+    enc = enc.cuda()
+    with pytest.raises(NotImplementedError):
+        enc(torch.zeros(1, 4, 64, device="cuda"), src_mask=torch.ones(1, 5, 5, device="cuda"))
+
+
+def test_batch1_inference_and_dataparallel_wrapper(M):
+    """The reference's eval loops call forward once per window (batch 1); nn.DataParallel wrapping must work."""
+    torch.manual_seed(0)
+    enc = M.Encoder(n_layers=1, n_head=2, d_k=64, d_v=64, d_model=128, d_inner=256, relative_pe=True, window_size=4,
+                    window_depth=3, MHA_layerNorm=True).cuda().eval()
+    cls = M.Classifier(128).cuda().eval()
+    x = torch.randn(4, 48, 128, device="cuda").abs()
+    with torch.no_grad():
+        full = cls(enc(x)[:, 0, :])
+        single = torch.cat([cls(enc(x[i:i + 1])[:, 0, :]) for i in range(4)])
+        short = enc(x[:1, :16])  # a 1-clip trailing window
+    abs_close("batch-1 == batched", single, full, 2e-3)
+    assert tuple(short.shape) == (1, 17, 128)
+    dp = torch.nn.DataParallel(enc)
+    with torch.no_grad():
+        out_dp = dp(x)
+    abs_close("DataParallel wrapper", out_dp, enc(x), 1e-6)
+    sd = dp.state_dict()
+    assert all(k.startswith("module.") for k in sd)
