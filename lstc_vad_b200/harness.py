@@ -184,20 +184,30 @@ class TrainStep:
     # -- MIL across ranks: all-gather the scores, evaluate the global loss everywhere, keep the local slice --
     def _global_mil(self, score: torch.Tensor, B: int, P: int, T: int, flat: bool):
         import torch.distributed as dist
-        n_local = score.numel()
-        half = n_local // 2
         flat_local = score.reshape(-1).contiguous()
         gathered = [torch.empty_like(flat_local) for _ in range(self.world)]
         dist.all_gather(gathered, flat_local.detach(), group=self.pg)
-        # reference order: all normal bags (rank-major), then all abnormal bags
-        glob = torch.cat([g[:half] for g in gathered] + [g[half:] for g in gathered])
+        glob = global_score_order(gathered)
         Bg = B * self.world
         spar_start = Bg if flat else Bg * P * T
         out3, _, dglob = ops.mil_loss(glob, Bg, P, T, 1, self.lambda_1, spar_start)
-        d_local = torch.cat([dglob[self.rank * half:(self.rank + 1) * half],
-                             dglob[Bg * P * T + self.rank * half: Bg * P * T + (self.rank + 1) * half]])
+        d_local = local_grad_slice(dglob, self.rank, self.world)
         mil = _InjectGrad.apply(flat_local, out3[0], d_local)
         return mil, out3[1], out3[2]
+
+
+def global_score_order(gathered: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Per-rank score vectors (each: this rank's normal windows then its abnormal windows) -> the reference's flat
+    order for the whole batch: every normal bag (rank-major) first, then every abnormal bag."""
+    half = gathered[0].numel() // 2
+    return torch.cat([g[:half] for g in gathered] + [g[half:] for g in gathered])
+
+
+def local_grad_slice(dglob: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Inverse of global_score_order for one rank: the gradient entries of this rank's windows, local order."""
+    half = dglob.numel() // (2 * world)
+    n_norm = half * world
+    return torch.cat([dglob[rank * half:(rank + 1) * half], dglob[n_norm + rank * half:n_norm + (rank + 1) * half]])
 
 
 class _InjectGrad(torch.autograd.Function):

@@ -30,3 +30,38 @@ def report(name, got, ref, rtol, atol):
 def assert_close(name, got, ref, rtol=2e-2, atol=2e-2):
     ok, msg = report(name, got, ref, rtol, atol)
     assert ok, msg
+
+
+def tensor_close(name, got, ref, rel_l2=3e-2, p999=6e-2, max_rel=0.3, floor=1e-6):
+    """Tolerance model for bf16-activation tensors (encoder outputs, gradients), all relative to max|ref|:
+         ||got - ref||_F / ||ref||_F <= rel_l2          (bulk error)
+         99.9 % of the elements within p999 * max|ref|  (no systematic layout error)
+         every element within max_rel * max|ref|        (isolated outliers come from ReLU-mask / dropout flips of
+                                                          pre-activations that sit within bf16 rounding of zero)
+    """
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    diff = (got - ref).abs()
+    scale = max(ref.abs().max().item(), floor)
+    l2 = (diff.double().pow(2).sum().sqrt() / max(ref.double().pow(2).sum().sqrt().item(), floor)).item()
+    flat = diff.flatten()
+    k = max(1, int(0.999 * flat.numel()))
+    q = flat.kthvalue(k).values.item() / scale
+    mx = flat.max().item() / scale
+    finite = bool(torch.isfinite(got).all())
+    msg = (f"{name}: shape={tuple(got.shape)} rel_l2={l2:.3e} p99.9={q:.3e} max={mx:.3e} (x max|ref|={scale:.3e}) "
+           f"finite={finite}")
+    print(msg, flush=True)
+    assert finite and l2 <= rel_l2 and q <= p999 and mx <= max_rel, msg
+
+
+def probs_close(name, got, ref, max_abs=1.5e-2, mean_abs=4e-3):
+    """Scores / probabilities: max-abs and mean-abs error (bf16 noise floor of the reference itself under
+    autocast: 3.4e-3 / 8e-4 at the ShanghaiTech shape)."""
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    d = (got - ref).abs()
+    msg = f"{name}: shape={tuple(got.shape)} max_abs={d.max().item():.3e} mean_abs={d.mean().item():.3e}"
+    print(msg, flush=True)
+    assert d.max().item() <= max_abs and d.mean().item() <= mean_abs, msg
