@@ -85,7 +85,8 @@ int lstc_relbias_scatter(const float* ddense, const int64_t* index, int64_t inde
  *   x : bf16 or fp32 [rows, D] ; y : bf16 or fp32 ; mean/rstd : fp32 [rows] saved for backward.
  * Backward: dx (bf16 or fp32) and, when drop_p > 0 and dx_drop != NULL, a second bf16 output
  * dx_drop = dropout_mask(seed,offset) * dx / (1-p) (the gradient entering the preceding
- * Linear whose output was dropped out).  dgamma/dbeta fp32 [D] are overwritten.
+ * Linear whose output was dropped out).  dgamma/dbeta fp32 [D] are overwritten.  dxsum (nullable) fp32 [D]
+ * receives the column sums of dx_drop (of dx when there is no dropout) = the bias gradient of that Linear.
  *   workspace: fp32, at least lstc_layernorm_bwd_workspace(rows, D) bytes.
  * Requirements: D % 8 == 0, D <= 8192.
  * ------------------------------------------------------------------------------------------- */
@@ -94,8 +95,8 @@ int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamma, const fl
 int64_t lstc_layernorm_bwd_workspace(int64_t rows, int64_t D);
 int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, int x_is_f32, const float* gamma,
                        const float* mean, const float* rstd, void* dx, int dx_is_f32, void* dx_drop,
-                       float drop_p, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta, void* workspace,
-                       int64_t rows, int64_t D, void* stream);
+                       float drop_p, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta, float* dxsum,
+                       void* workspace, int64_t rows, int64_t D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * CLS-token prepend (+ optional learned absolute position encoding and its dropout):

@@ -30,7 +30,7 @@ SIGNATURES: dict[str, tuple] = {
     "lstc_relbias_scatter": (_I, [_P, _P, _L, _I, _I, _L, _P, _P]),
     "lstc_layernorm_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _L, _L, _F, _P]),
     "lstc_layernorm_bwd_workspace": (_L, [_L, _L]),
-    "lstc_layernorm_bwd": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _F, _U, _U, _P, _P, _P, _L, _L, _P]),
+    "lstc_layernorm_bwd": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _F, _U, _U, _P, _P, _P, _P, _L, _L, _P]),
     "lstc_cls_prepend_fwd": (_I, [_P, _I, _P, _P, _F, _U, _U, _P, _L, _L, _L, _P]),
     "lstc_cls_prepend_bwd": (_I, [_P, _I, _F, _U, _U, _P, _P, _P, _L, _L, _L, _P]),
     "lstc_head_tail_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _U, _U, _P, _P, _P]),

@@ -5,12 +5,17 @@
 //   O = P v ; O.transpose(1,2).contiguous().view(W, L, H*dv)
 // and its autograd backward.
 //
-// Grid = (window groups, heads).  A CTA owns one head and walks over windows; the whole
-// Q/K/V (and dO) tile of a (window, head) pair sits in shared memory (XOR-swizzled 16-byte
-// chunks, conflict-free for ldmatrix), the [L,L] score tile lives in registers, softmax uses
-// quad shuffles, dropout is regenerated from Philox, and the rel-pos bias / its gradient stay
-// in registers across the windows of the CTA (one atomic flush per CTA for dbias).
-// Warp w of the CTA owns query rows [16w, 16w+16).
+// Grid = (window groups, heads).  A CTA owns one head and walks over windows.  Q/K/V (and dO) are
+// streamed through shared memory in [L x 64-column] chunk tiles by a multi-stage cp.async ring that runs
+// ahead across window boundaries, so HBM stays busy while the tensor cores work (the CTA never holds a
+// whole [L x dk] tile: ~56-74 KB of smem, 3-4 CTAs per SM):
+//   forward : S  += Q_c K_c^T (c = 0..dk/64-1) -> softmax / dropout in registers -> O_c = P V_c
+//   backward: S  += Q_c K_c^T ; dP += dO_c V_c^T -> P, dS in registers, bf16 copies in smem ->
+//             dQ_c = dS K_c ; dK_c = dS^T Q_c ; dV_c = P^T dO_c      (K, Q, dO chunks re-read through L2)
+// Math runs on mma.sync.m16n8k16 bf16 (tiles of <= 96 rows are too small for a 128-row tcgen05 tile), fp32
+// accumulation, softmax by quad shuffles, dropout regenerated from Philox, rel-pos bias read from a dense
+// [H,L,L] table, its gradient accumulated in registers across the windows of the CTA (one atomic flush).
+// Warp w of the CTA owns query rows [16w, 16w+16) (and key rows [16w, 16w+16) of dK / dV).
 #include "common.cuh"
 #include "../../include/lstc_vad_b200.h"
 
@@ -57,12 +62,9 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-// byte offset of 16-byte chunk c16 of row r inside a [rows][DK] bf16 tile (row pitch DK*2 bytes),
-// chunk index XOR-swizzled with the row so 8 consecutive rows of one chunk hit 8 distinct bank groups
-template <int DK>
-__device__ __forceinline__ uint32_t tile_off(int r, int c16) {
-  return (uint32_t)(r * (DK * 2) + ((c16 ^ (r & 7)) << 4));
-}
+// byte offset of 16-byte chunk c16 (0..7) of row r inside a [rows][64] bf16 chunk tile (128-byte rows); the chunk
+// index is XOR-swizzled with the row so the 8 rows of one ldmatrix phase hit 8 distinct bank groups
+__device__ __forceinline__ uint32_t ct_off(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
 struct Params {
   const __nv_bfloat16* qkv;
@@ -82,58 +84,74 @@ struct Params {
   float* dbias;  // bwd optional
 };
 
-// Loads the [L, DK] slab starting at `src` (row pitch ld elements) into a swizzled smem tile, zero-filling
-// rows L..LP-1.
-template <int LP, int DK>
-__device__ __forceinline__ void load_tile(uint32_t s_tile, const __nv_bfloat16* src, int64_t ld, int L) {
-  constexpr int CH = DK / 8;
-  for (int idx = threadIdx.x; idx < LP * CH; idx += blockDim.x) {
-    const int r = idx / CH, c = idx % CH;
+// cp.async of one [L x 64] column chunk starting at `src` (row pitch ld elements); rows L..LP-1 are zero-filled
+template <int LP>
+__device__ __forceinline__ void load_chunk_tile(uint32_t s_tile, const __nv_bfloat16* src, int64_t ld, int L) {
+  for (int idx = threadIdx.x; idx < LP * 8; idx += LP * 2 /* = blockDim.x */) {
+    const int r = idx >> 3, c = idx & 7;
     const bool valid = r < L;
-    cp_async16(s_tile + tile_off<DK>(r, c), valid ? (const void*)(src + (int64_t)r * ld + c * 8) : (const void*)src,
+    cp_async16(s_tile + ct_off(r, c), valid ? (const void*)(src + (int64_t)r * ld + c * 8) : (const void*)src,
                valid ? 16 : 0);
   }
 }
 
-// S (this warp's 16 query rows x LP keys) = A_tile[m0.., :] * B_tile^T, both tiles [rows][DK] with DK contiguous
-template <int LP, int DK>
-__device__ __forceinline__ void mma_rows_x_rowsT(float (&s)[LP / 8][4], uint32_t sA, uint32_t sB, int m0, int lane) {
+// acc (this warp's 16 rows x LP) += A_c[m0.., 0:64] * B_c[:, 0:64]^T, both chunk tiles [rows][64] (k contiguous)
+template <int LP>
+__device__ __forceinline__ void mma_acc_rows_x_rowsT(float (&acc)[LP / 8][4], uint32_t sA, uint32_t sB, int m0, int lane) {
 #pragma unroll
-  for (int n = 0; n < LP / 8; ++n) {
-    s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f;
-  }
-#pragma unroll 4
-  for (int kk = 0; kk < DK / 16; ++kk) {
+  for (int kk = 0; kk < 4; ++kk) {
     uint32_t a[4];
-    ldsm_x4(sA + tile_off<DK>(m0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)), a);
+    ldsm_x4(sA + ct_off(m0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)), a);
 #pragma unroll
     for (int np = 0; np < LP / 16; ++np) {
       uint32_t b[4];
-      ldsm_x4(sB + tile_off<DK>(np * 16 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1)), b);
-      mma16816(s[2 * np], a, b[0], b[1]);
-      mma16816(s[2 * np + 1], a, b[2], b[3]);
+      ldsm_x4(sB + ct_off(np * 16 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1)), b);
+      mma16816(acc[2 * np], a, b[0], b[1]);
+      mma16816(acc[2 * np + 1], a, b[2], b[3]);
     }
   }
 }
 
-// Softmax over the key axis of the warp's score fragment (in place), then dropout.
-//   on return: p  = softmax probabilities (pre-dropout)
-//              pd = post-dropout probabilities (p * keep / (1-p_drop))
+// acc[8 n-tiles][4] (16 rows x 64 cols) = sum over k-tiles of A-frags * B_c[k rows][64 cols]  (B rows = k, cols
+// contiguous => ldmatrix.trans)
+template <int KT>
+__device__ __forceinline__ void mma_frag_x_rows(float (&acc)[8][4], const uint32_t (&afr)[KT][4], uint32_t sB, int lane) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(sB + ct_off(j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)), b);
+      mma16816(acc[2 * np], afr[j], b[0], b[1]);
+      mma16816(acc[2 * np + 1], afr[j], b[2], b[3]);
+    }
+  }
+}
+
+// Scale, add bias, mask, softmax over the key axis of the warp's score fragment (in place) and draw the dropout
+// mask.  On return s = softmax probabilities (pre-dropout); keep[r] bit (2n+e) tells whether element (row r, n-tile
+// n, e) survives dropout (all ones when dropout is off).  dropped(s, keep) gives the post-dropout probability.
 template <int LP>
-__device__ __forceinline__ void softmax_dropout(float (&s)[LP / 8][4], float (&pd)[LP / 8][4],
-                                                const float (&bfr)[LP / 8][4], const Params& p, int64_t w, int h,
-                                                int m0, int lane) {
+__device__ __forceinline__ void softmax_dropout(float (&s)[LP / 8][4], uint32_t (&keep)[2], const Params& p, int64_t w,
+                                                int h, int m0, int lane) {
   const int g = lane >> 2, t = lane & 3;
   constexpr float LOG2E = 1.4426950408889634f;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
+    const int row = m0 + g + 8 * r;
+    const float* brow = (p.bias != nullptr && row < p.L) ? p.bias + ((int64_t)h * p.L + row) * p.L : nullptr;
     float mx = -INFINITY;
 #pragma unroll
     for (int n = 0; n < LP / 8; ++n) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = n * 8 + 2 * t + e;
-        float v = s[n][2 * r + e] * p.scale + bfr[n][2 * r + e];
+        float v = s[n][2 * r + e] * p.scale;
+        if (brow != nullptr && col < p.L) v += __ldg(brow + col);
         v = col < p.L ? v : -INFINITY;
         s[n][2 * r + e] = v;
         mx = fmaxf(mx, v);
@@ -154,93 +172,150 @@ __device__ __forceinline__ void softmax_dropout(float (&s)[LP / 8][4], float (&p
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     const float inv = 1.0f / sum;
-    const int row = m0 + g + 8 * r;
     const int64_t grow = (w * p.H + h) * (int64_t)p.L + row;
     const int64_t ld8 = (p.L + 7) >> 3;
+    uint32_t kb = 0xffffffffu;
 #pragma unroll
     for (int n = 0; n < LP / 8; ++n) {
-      const float p0 = s[n][2 * r] * inv, p1 = s[n][2 * r + 1] * inv;
-      s[n][2 * r] = p0;
-      s[n][2 * r + 1] = p1;
-      float d0 = p0, d1 = p1;
+      s[n][2 * r] *= inv;
+      s[n][2 * r + 1] *= inv;
       if (p.drop_p > 0.f && row < p.L && n * 8 < p.L) {
-        const uint32_t keep = dropout_keep8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), p.drop_thr16);
-        d0 = ((keep >> (2 * t)) & 1u) ? p0 * p.drop_scale : 0.f;
-        d1 = ((keep >> (2 * t + 1)) & 1u) ? p1 * p.drop_scale : 0.f;
+        const uint32_t k8 = dropout_keep8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), p.drop_thr16);
+        const uint32_t two = (k8 >> (2 * t)) & 3u;
+        kb = (kb & ~(3u << (2 * n))) | (two << (2 * n));
       }
-      pd[n][2 * r] = d0;
-      pd[n][2 * r + 1] = d1;
     }
+    keep[r] = kb;
   }
 }
+// post-dropout probability of fragment element (n, i) with i = 2r+e
+__device__ __forceinline__ float dropped(float pr, const uint32_t (&keep)[2], int n, int i, float scale) {
+  return ((keep[i >> 1] >> (2 * n + (i & 1))) & 1u) ? pr * scale : 0.f;
+}
 
-template <int LP>
-__device__ __forceinline__ void load_bias_frag(float (&bfr)[LP / 8][4], const float* bias, int h, int L, int m0,
-                                               int lane) {
+// ------------------------------------------------------------------------------------------
+// cp.async stage ring shared by both kernels.  A stage holds two [LP x 64] chunk tiles.
+//   PHASES x NC stages per window; phase ph, chunk c loads tile0 / tile1 from the tensors listed below.
+// ------------------------------------------------------------------------------------------
+template <int LP, int DK, int NS, bool BWD>
+struct Ring {
+  static constexpr int NC = DK / 64;
+  static constexpr int CT = LP * 128;
+  static constexpr int STAGE = 2 * CT;
+  static constexpr int SPW = (BWD ? 4 : 2) * NC;  // stages per window
+
+  const Params& p;
+  uint32_t base;
+  int h;
+  int64_t n_it;        // windows this CTA processes
+  int64_t g_issue;     // next stage to issue
+  int64_t g_total;
+
+  __device__ Ring(const Params& p_, uint32_t base_, int h_) : p(p_), base(base_), h(h_) {
+    n_it = (p.W - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
+    if (n_it < 0) n_it = 0;
+    g_issue = 0;
+    g_total = n_it * SPW;
+  }
+  __device__ uint32_t tile(int64_t g, int which) const { return base + (uint32_t)(g % NS) * STAGE + which * CT; }
+
+  __device__ void issue_next() {
+    const int64_t g = g_issue++;
+    if (g < g_total) {
+      const int64_t it = g / SPW;
+      const int s = (int)(g % SPW);
+      const int ph = s / NC, c = s % NC;
+      const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
+      const int HD = p.H * DK;
+      const __nv_bfloat16* q = p.qkv + (w * p.L) * p.ld + h * DK + c * 64;
+      const uint32_t t0 = tile(g, 0), t1 = tile(g, 1);
+      if (!BWD) {
+        if (ph == 0) {
+          load_chunk_tile<LP>(t0, q, p.ld, p.L);
+          load_chunk_tile<LP>(t1, q + HD, p.ld, p.L);
+        } else {
+          load_chunk_tile<LP>(t0, q + 2 * HD, p.ld, p.L);
+        }
+      } else {
+        const __nv_bfloat16* d_o = p.dout + (w * p.L) * p.ld_dout + h * DK + c * 64;
+        if (ph == 0) {
+          load_chunk_tile<LP>(t0, q, p.ld, p.L);
+          load_chunk_tile<LP>(t1, q + HD, p.ld, p.L);
+        } else if (ph == 1) {
+          load_chunk_tile<LP>(t0, d_o, p.ld_dout, p.L);
+          load_chunk_tile<LP>(t1, q + 2 * HD, p.ld, p.L);
+        } else if (ph == 2) {
+          load_chunk_tile<LP>(t0, q + HD, p.ld, p.L);  // K_c
+          load_chunk_tile<LP>(t1, q, p.ld, p.L);       // Q_c
+        } else {
+          load_chunk_tile<LP>(t0, d_o, p.ld_dout, p.L);
+        }
+      }
+    }
+    cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
+  }
+  __device__ void prologue() {
+#pragma unroll
+    for (int i = 0; i < NS - 1; ++i) issue_next();
+  }
+  // Makes stage g resident and visible to all warps, then refills the slot consumed one step earlier.
+  __device__ void acquire() {
+    cp_async_wait<NS - 2>();
+    __syncthreads();
+    issue_next();
+  }
+};
+
+// writes a finished 16x64 fp32 fragment block (rows row0.., 64 columns at gbase) as bf16: each quad stores 16
+// contiguous bytes per row and n-tile; L2 merges the two halves of a 32-byte sector before it reaches HBM
+__device__ __forceinline__ void store_chunk(const float (&acc)[8][4], float mul, __nv_bfloat16* gbase, int64_t ld_out,
+                                            int row0, int L, int lane) {
   const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int n = 0; n < LP / 8; ++n) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int row = m0 + g + ((e >> 1) << 3);
-      const int col = n * 8 + 2 * t + (e & 1);
-      bfr[n][e] = (bias != nullptr && row < L && col < L) ? __ldg(bias + ((int64_t)h * L + row) * L + col) : 0.f;
-    }
-  }
-}
-
-// acc[8 n-tiles][4] (16 rows x 64 cols) = sum over k-tiles of A-frags * B_tile[k rows][chunk cols] (B rows = k,
-// cols contiguous => ldmatrix.trans).
-template <int KT, int DK>
-__device__ __forceinline__ void mma_frag_x_rows(float (&acc)[8][4], const uint32_t (&afr)[KT][4], uint32_t sB,
-                                                int chunk, int lane) {
+  const int r0 = row0 + g, r1 = row0 + g + 8;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
-    acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f;
-  }
-#pragma unroll
-  for (int j = 0; j < KT; ++j) {
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t b[4];
-      ldsm_x4_t(sB + tile_off<DK>(j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chunk * 8 + np * 2 + (lane >> 4)), b);
-      mma16816(acc[2 * np], afr[j], b[0], b[1]);
-      mma16816(acc[2 * np + 1], afr[j], b[2], b[3]);
-    }
+    if (r0 < L)
+      *reinterpret_cast<uint32_t*>(gbase + (int64_t)r0 * ld_out + n * 8 + 2 * t) = pack_bf16x2(acc[n][0] * mul, acc[n][1] * mul);
+    if (r1 < L)
+      *reinterpret_cast<uint32_t*>(gbase + (int64_t)r1 * ld_out + n * 8 + 2 * t) = pack_bf16x2(acc[n][2] * mul, acc[n][3] * mul);
   }
 }
 
 // ==========================================================================================
 // Forward
 // ==========================================================================================
-template <int LP, int DK>
+template <int LP, int DK, int NS>
 __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) {
-  constexpr int NT = LP / 8, KT = LP / 16, TILE = LP * DK * 2, CH = DK / 8;
+  constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
+  using R = Ring<LP, DK, NS, false>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE, sV = sK + TILE;
+  const uint32_t s0 = smem_u32(smem);
   const int h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = warp * 16;
-  const int HD = p.H * DK;
-
-  float bfr[NT][4];
-  load_bias_frag<LP>(bfr, p.bias, h, p.L, m0, lane);
-
-  for (int64_t w = blockIdx.x; w < p.W; w += gridDim.x) {
-    const __nv_bfloat16* base = p.qkv + (w * p.L) * p.ld + h * DK;
-    load_tile<LP, DK>(sQ, base, p.ld, p.L);
-    load_tile<LP, DK>(sK, base + HD, p.ld, p.L);
-    cp_async_commit();
-    load_tile<LP, DK>(sV, base + 2 * HD, p.ld, p.L);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-
-    float s[NT][4], pd[NT][4];
-    mma_rows_x_rowsT<LP, DK>(s, sQ, sK, m0, lane);
-    softmax_dropout<LP>(s, pd, bfr, p, w, h, m0, lane);
-
+  R ring(p, s0, h);
+  ring.prologue();
+  int64_t gi = 0;
+  for (int64_t it = 0; it < ring.n_it; ++it) {
+    const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
+    float s[NT][4];
+    uint32_t keep[2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f;
+    }
+#pragma unroll 1
+    for (int c = 0; c < R::NC; ++c, ++gi) {
+      ring.acquire();
+      mma_acc_rows_x_rowsT<LP>(s, ring.tile(gi, 0), ring.tile(gi, 1), m0, lane);
+    }
+    softmax_dropout<LP>(s, keep, p, w, h, m0, lane);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[n][e] = dropped(s[n][e], keep, n, e, p.drop_scale);  // s = post-dropout P
+    }
     if (p.probs != nullptr) {
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
@@ -248,197 +323,159 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) 
         for (int e = 0; e < 4; ++e) {
           const int row = m0 + g + ((e >> 1) << 3);
           const int col = n * 8 + 2 * t + (e & 1);
-          if (row < p.L && col < p.L) p.probs[((w * p.H + h) * (int64_t)p.L + row) * p.L + col] = pd[n][e];
+          if (row < p.L && col < p.L) p.probs[((w * p.H + h) * (int64_t)p.L + row) * p.L + col] = s[n][e];
         }
       }
     }
     uint32_t pa[KT][4];
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-      pa[j][0] = pack_bf16x2(pd[2 * j][0], pd[2 * j][1]);
-      pa[j][1] = pack_bf16x2(pd[2 * j][2], pd[2 * j][3]);
-      pa[j][2] = pack_bf16x2(pd[2 * j + 1][0], pd[2 * j + 1][1]);
-      pa[j][3] = pack_bf16x2(pd[2 * j + 1][2], pd[2 * j + 1][3]);
+      pa[j][0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      pa[j][1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      pa[j][2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[j][3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
     }
-    cp_async_wait<0>();
-    __syncthreads();
-
+    __nv_bfloat16* obase = p.out + (w * p.L) * p.ld_out + h * DK;
 #pragma unroll 1
-    for (int chunk = 0; chunk < DK / 64; ++chunk) {
+    for (int c = 0; c < R::NC; ++c, ++gi) {
+      ring.acquire();
       float o[8][4];
-      mma_frag_x_rows<KT, DK>(o, pa, sV, chunk, lane);
-      // stage into this warp's (now dead) Q rows
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        st_shared_b32(sQ + tile_off<DK>(m0 + g, chunk * 8 + n) + 4 * t, pack_bf16x2(o[n][0], o[n][1]));
-        st_shared_b32(sQ + tile_off<DK>(m0 + g + 8, chunk * 8 + n) + 4 * t, pack_bf16x2(o[n][2], o[n][3]));
-      }
+      mma_frag_x_rows<KT>(o, pa, ring.tile(gi, 0), lane);
+      store_chunk(o, 1.0f, obase + c * 64, p.ld_out, m0, p.L, lane);
     }
-    __syncwarp();
-    for (int idx = lane; idx < 16 * CH; idx += 32) {
-      const int r = m0 + idx / CH, c = idx % CH;
-      if (r < p.L) {
-        const uint4 v = ld_shared_v4(sQ + tile_off<DK>(r, c));
-        *reinterpret_cast<uint4*>(p.out + (w * p.L + r) * p.ld_out + h * DK + c * 8) = v;
-      }
-    }
-    __syncthreads();  // tiles are overwritten by the next window's loads
   }
+  cp_async_wait<0>();
+  (void)NW;
 }
 
 // ==========================================================================================
 // Backward
 // ==========================================================================================
-// smem: Q | K | V | dO tiles, then per-warp 16x64 staging.  After phase 1 the V tile is dead and is
-// re-used for the bf16 copies of Pd (post-dropout probs) and dS, [LP][LP+8] each.
-template <int LP, int DK>
-__global__ void __launch_bounds__(LP / 16 * 32) attn_bwd_kernel(const Params p) {
-  constexpr int NT = LP / 8, KT = LP / 16, TILE = LP * DK * 2, NW = LP / 16;
-  constexpr int PP = (LP + 8) * 2;  // padded row pitch (bytes) of the Pd / dS tiles
-  constexpr bool ALIAS_V = (2 * LP * PP <= TILE);  // else Pd/dS get their own region after the staging
+template <int LP, int DK, int NS>
+__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kernel(const Params p) {
+  constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
+  constexpr int PP = (LP + 8) * 2;  // padded row pitch (bytes) of the bf16 Pd / dS tiles
+  using R = Ring<LP, DK, NS, true>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE, sV = sK + TILE, sDO = sV + TILE;
-  const uint32_t sStage = sDO + TILE + (threadIdx.x >> 5) * 2048;  // 16 rows x 128 B per warp
-  const uint32_t sPd = ALIAS_V ? sV : (sDO + TILE + NW * 2048), sDS = sPd + LP * PP;
+  const uint32_t s0 = smem_u32(smem);
   const int h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = warp * 16;
   const int HD = p.H * DK;
+  const uint32_t sPd = s0 + NS * R::STAGE, sDS = sPd + LP * PP;
 
-  float bfr[NT][4], dbacc[NT][4];
-  load_bias_frag<LP>(bfr, p.bias, h, p.L, m0, lane);
+  float dbacc[NT][4];
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     dbacc[n][0] = 0.f; dbacc[n][1] = 0.f; dbacc[n][2] = 0.f; dbacc[n][3] = 0.f;
   }
-
-  // writes a finished 16x64 fp32 fragment block (rows row0.., cols chunk*64..) to global through the staging tile
-  auto store_chunk = [&](const float (&acc)[8][4], float mul, __nv_bfloat16* gbase, int row0, int chunk) {
-    __syncwarp();
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      st_shared_b32(sStage + g * 128 + ((n ^ (g & 7)) << 4) + 4 * t, pack_bf16x2(acc[n][0] * mul, acc[n][1] * mul));
-      st_shared_b32(sStage + (g + 8) * 128 + ((n ^ (g & 7)) << 4) + 4 * t,
-                    pack_bf16x2(acc[n][2] * mul, acc[n][3] * mul));
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = lane + 32 * i;
-      const int r = idx >> 3, c = idx & 7;
-      if (row0 + r < p.L) {
-        const uint4 v = ld_shared_v4(sStage + r * 128 + ((c ^ (r & 7)) << 4));
-        *reinterpret_cast<uint4*>(gbase + (int64_t)(row0 + r) * p.ld_out + chunk * 64 + c * 8) = v;
-      }
-    }
-  };
-
-  for (int64_t w = blockIdx.x; w < p.W; w += gridDim.x) {
-    const __nv_bfloat16* base = p.qkv + (w * p.L) * p.ld + h * DK;
-    load_tile<LP, DK>(sQ, base, p.ld, p.L);
-    load_tile<LP, DK>(sK, base + HD, p.ld, p.L);
-    cp_async_commit();
-    load_tile<LP, DK>(sV, base + 2 * HD, p.ld, p.L);
-    load_tile<LP, DK>(sDO, p.dout + (w * p.L) * p.ld_dout + h * DK, p.ld_dout, p.L);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-
-    // ---- phase 1: P, dP, dS for this warp's query rows ----
-    float s[NT][4], pd[NT][4];
-    mma_rows_x_rowsT<LP, DK>(s, sQ, sK, m0, lane);
-    softmax_dropout<LP>(s, pd, bfr, p, w, h, m0, lane);  // s = P, pd = dropped P
-    cp_async_wait<0>();
-    __syncthreads();
-    float dp[NT][4];
-    mma_rows_x_rowsT<LP, DK>(dp, sDO, sV, m0, lane);  // dP_d = dO V^T
-    // dropout backward + softmax backward:  dS = P * (dP - sum_j P dP)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float delta = 0.f;
+  R ring(p, s0, h);
+  ring.prologue();
+  int64_t gi = 0;
+  for (int64_t it = 0; it < ring.n_it; ++it) {
+    const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
+    {
+      // ---- phase A: S = Q K^T, dP = dO V^T for this warp's query rows ----
+      float s[NT][4], dp[NT][4];
+      uint32_t keep[2];
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
+        s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f;
+        dp[n][0] = 0.f; dp[n][1] = 0.f; dp[n][2] = 0.f; dp[n][3] = 0.f;
+      }
+#pragma unroll 1
+      for (int c = 0; c < R::NC; ++c, ++gi) {
+        ring.acquire();
+        mma_acc_rows_x_rowsT<LP>(s, ring.tile(gi, 0), ring.tile(gi, 1), m0, lane);
+      }
+#pragma unroll 1
+      for (int c = 0; c < R::NC; ++c, ++gi) {
+        ring.acquire();
+        mma_acc_rows_x_rowsT<LP>(dp, ring.tile(gi, 0), ring.tile(gi, 1), m0, lane);
+      }
+      softmax_dropout<LP>(s, keep, p, w, h, m0, lane);  // s = P, keep = dropout mask bits
+      // dropout backward + softmax backward:  dS = P * (dP - sum_j P dP)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = 2 * r + e;
-          // d/dP of the dropped prob: keep/(1-p) == pd/P when P > 0 ; use the mask implied by pd
-          const float dpm = (p.drop_p > 0.f) ? (pd[n][i] != 0.f ? dp[n][i] * p.drop_scale : 0.f) : dp[n][i];
-          dp[n][i] = dpm;
-          delta += s[n][i] * dpm;
+      for (int r = 0; r < 2; ++r) {
+        float delta = 0.f;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 2 * r + e;
+            const float dpm = dropped(dp[n][i], keep, n, i, p.drop_scale);
+            dp[n][i] = dpm;
+            delta += s[n][i] * dpm;
+          }
+        }
+        delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 2 * r + e;
+            const int row = m0 + g + 8 * r, col = n * 8 + 2 * t + e;
+            float ds = s[n][i] * (dp[n][i] - delta);
+            ds = (row < p.L && col < p.L) ? ds : 0.f;
+            dp[n][i] = ds;  // dp now holds dS
+            if (row >= 1 && col >= 1) dbacc[n][i] += ds;
+          }
         }
       }
-      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
-      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+      // bf16 copies for the transposed products of phase B (previous window's readers are >= 8 barriers behind)
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = 2 * r + e;
-          const int row = m0 + g + 8 * r, col = n * 8 + 2 * t + e;
-          float ds = s[n][i] * (dp[n][i] - delta);
-          ds = (row < p.L && col < p.L) ? ds : 0.f;
-          dp[n][i] = ds;  // dp now holds dS
-          if (row >= 1 && col >= 1) dbacc[n][i] += ds;
-        }
+        const uint32_t cb = (n * 8 + 2 * t) * 2;
+        st_shared_b32(sPd + (m0 + g) * PP + cb, pack_bf16x2(dropped(s[n][0], keep, n, 0, p.drop_scale),
+                                                            dropped(s[n][1], keep, n, 1, p.drop_scale)));
+        st_shared_b32(sPd + (m0 + g + 8) * PP + cb, pack_bf16x2(dropped(s[n][2], keep, n, 2, p.drop_scale),
+                                                                dropped(s[n][3], keep, n, 3, p.drop_scale)));
+        st_shared_b32(sDS + (m0 + g) * PP + cb, pack_bf16x2(dp[n][0], dp[n][1]));
+        st_shared_b32(sDS + (m0 + g + 8) * PP + cb, pack_bf16x2(dp[n][2], dp[n][3]));
       }
     }
-    __syncthreads();  // every warp is done reading V before it is overwritten by Pd / dS
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const uint32_t c = (n * 8 + 2 * t) * 2;
-      st_shared_b32(sPd + (m0 + g) * PP + c, pack_bf16x2(pd[n][0], pd[n][1]));
-      st_shared_b32(sPd + (m0 + g + 8) * PP + c, pack_bf16x2(pd[n][2], pd[n][3]));
-      st_shared_b32(sDS + (m0 + g) * PP + c, pack_bf16x2(dp[n][0], dp[n][1]));
-      st_shared_b32(sDS + (m0 + g + 8) * PP + c, pack_bf16x2(dp[n][2], dp[n][3]));
-    }
-    __syncthreads();
-
-    // ---- phase 2 ----
+    // ---- phase B ----
     __nv_bfloat16* dq_base = p.out + (w * p.L) * p.ld_out + h * DK;
     __nv_bfloat16* dk_base = dq_base + HD;
     __nv_bfloat16* dv_base = dq_base + 2 * HD;
     {
-      // dQ[i,:] = scale * sum_j dS[i,j] K[j,:]        (A = dS rows i, non-transposed)
-      uint32_t afr[KT][4];
-#pragma unroll
-      for (int j = 0; j < KT; ++j)
-        ldsm_x4(sDS + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * PP + (j * 16 + (lane >> 4) * 8) * 2, afr[j]);
+      uint32_t a_ds[KT][4], a_dst[KT][4];
 #pragma unroll 1
-      for (int chunk = 0; chunk < DK / 64; ++chunk) {
+      for (int c = 0; c < R::NC; ++c, ++gi) {
+        ring.acquire();  // its barrier also publishes Pd / dS of every warp
+        if (c == 0) {
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            // A = dS rows of this warp (row i, k = j)
+            ldsm_x4(sDS + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * PP + (j * 16 + (lane >> 4) * 8) * 2, a_ds[j]);
+            // A = dS^T rows of this warp (row j, k = i): transposed ldmatrix of dS[i][j]
+            ldsm_x4_t(sDS + (j * 16 + (lane & 7) + (lane >> 4) * 8) * PP + (m0 + ((lane >> 3) & 1) * 8) * 2, a_dst[j]);
+          }
+        }
         float acc[8][4];
-        mma_frag_x_rows<KT, DK>(acc, afr, sK, chunk, lane);
-        store_chunk(acc, p.scale, dq_base, m0, chunk);
+        mma_frag_x_rows<KT>(acc, a_ds, ring.tile(gi, 0), lane);   // dQ_c = scale * dS K_c
+        store_chunk(acc, p.scale, dq_base + c * 64, p.ld_out, m0, p.L, lane);
+        mma_frag_x_rows<KT>(acc, a_dst, ring.tile(gi, 1), lane);  // dK_c = scale * dS^T Q_c
+        store_chunk(acc, p.scale, dk_base + c * 64, p.ld_out, m0, p.L, lane);
       }
     }
     {
-      // dK[j,:] = scale * sum_i dS[i,j] Q[i,:]        (A = dS^T: transposed ldmatrix of dS[i][j])
-      uint32_t afr[KT][4];
+      uint32_t a_pdt[KT][4];
 #pragma unroll
       for (int i = 0; i < KT; ++i)
-        ldsm_x4_t(sDS + (i * 16 + (lane & 7) + (lane >> 4) * 8) * PP + (m0 + ((lane >> 3) & 1) * 8) * 2, afr[i]);
+        ldsm_x4_t(sPd + (i * 16 + (lane & 7) + (lane >> 4) * 8) * PP + (m0 + ((lane >> 3) & 1) * 8) * 2, a_pdt[i]);
 #pragma unroll 1
-      for (int chunk = 0; chunk < DK / 64; ++chunk) {
+      for (int c = 0; c < R::NC; ++c, ++gi) {
+        ring.acquire();
         float acc[8][4];
-        mma_frag_x_rows<KT, DK>(acc, afr, sQ, chunk, lane);
-        store_chunk(acc, p.scale, dk_base, m0, chunk);
+        mma_frag_x_rows<KT>(acc, a_pdt, ring.tile(gi, 0), lane);  // dV_c = Pd^T dO_c
+        store_chunk(acc, 1.0f, dv_base + c * 64, p.ld_out, m0, p.L, lane);
       }
     }
-    {
-      // dV[j,:] = sum_i Pd[i,j] dO[i,:]
-      uint32_t afr[KT][4];
-#pragma unroll
-      for (int i = 0; i < KT; ++i)
-        ldsm_x4_t(sPd + (i * 16 + (lane & 7) + (lane >> 4) * 8) * PP + (m0 + ((lane >> 3) & 1) * 8) * 2, afr[i]);
-#pragma unroll 1
-      for (int chunk = 0; chunk < DK / 64; ++chunk) {
-        float acc[8][4];
-        mma_frag_x_rows<KT, DK>(acc, afr, sDO, chunk, lane);
-        store_chunk(acc, 1.0f, dv_base, m0, chunk);
-      }
-    }
-    __syncthreads();  // tiles are overwritten by the next window's loads
   }
+  cp_async_wait<0>();
 
   if (p.dbias != nullptr) {
 #pragma unroll
@@ -452,38 +489,44 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_bwd_kernel(const Params p) 
       }
     }
   }
-  (void)NW;
 }
 
 // ------------------------------------------------------------------------------------------
-template <int LP, int DK>
-static int launch_fwd(const Params& p, cudaStream_t stream) {
-  constexpr int SMEM = 3 * LP * DK * 2;
-  auto kern = attn_fwd_kernel<LP, DK>;
-  LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  int per_sm = (227 * 1024) / (SMEM + 1024);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  int64_t gx = ((int64_t)num_sms() * per_sm + p.H - 1) / p.H;
-  if (gx > p.W) gx = p.W;
-  if (gx < 1) gx = 1;
-  kern<<<dim3((unsigned)gx, (unsigned)p.H), LP / 16 * 32, SMEM, stream>>>(p);
-  LSTC_CHECK_LAUNCH();
-  return LSTC_OK;
-}
-template <int LP, int DK>
-static int launch_bwd(const Params& p, cudaStream_t stream) {
-  constexpr int PDS = 2 * LP * (LP + 8) * 2;
-  constexpr int SMEM = 4 * LP * DK * 2 + (LP / 16) * 2048 + (PDS <= LP * DK * 2 ? 0 : PDS);
-  auto kern = attn_bwd_kernel<LP, DK>;
-  LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  int per_sm = (227 * 1024) / (SMEM + 1024);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  int64_t gx = ((int64_t)num_sms() * per_sm + p.H - 1) / p.H;
-  if (gx > p.W) gx = p.W;
-  if (gx < 1) gx = 1;
-  kern<<<dim3((unsigned)gx, (unsigned)p.H), LP / 16 * 32, SMEM, stream>>>(p);
+template <int LP, int DK, bool BWD>
+static int launch(const Params& p, cudaStream_t stream) {
+  constexpr int NS = 3;
+  constexpr int NW = LP / 16;
+  constexpr int STAGE = 2 * LP * 128;
+  constexpr int SMEM = NS * STAGE + (BWD ? 2 * LP * (LP + 8) * 2 : 0);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  LSTC_CHECK_CUDA(cudaGetDevice(&dev));
+  static int CTAS_PER_SM = 0;  // resident CTAs per SM for this instantiation (occupancy API: smem + registers)
+  if (BWD) {
+    auto kern = attn_bwd_kernel<LP, DK, NS>;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    if (CTAS_PER_SM == 0) LSTC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&CTAS_PER_SM, kern, NW * 32, SMEM));
+    // whole grid co-resident (a partial second wave would double the kernel time): round DOWN
+    int64_t gx = ((int64_t)num_sms() * (CTAS_PER_SM > 0 ? CTAS_PER_SM : 1)) / p.H;
+    if (gx < 1) gx = 1;
+    if (gx > p.W) gx = p.W;
+    kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p);
+  } else {
+    auto kern = attn_fwd_kernel<LP, DK, NS>;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    if (CTAS_PER_SM == 0) LSTC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&CTAS_PER_SM, kern, NW * 32, SMEM));
+    // whole grid co-resident (a partial second wave would double the kernel time): round DOWN
+    int64_t gx = ((int64_t)num_sms() * (CTAS_PER_SM > 0 ? CTAS_PER_SM : 1)) / p.H;
+    if (gx < 1) gx = 1;
+    if (gx > p.W) gx = p.W;
+    kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p);
+  }
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
@@ -491,8 +534,8 @@ static int launch_bwd(const Params& p, cudaStream_t stream) {
 template <int DK>
 static int dispatch_lp(bool bwd, const Params& p, cudaStream_t stream) {
   const int L = p.L;
-#define LSTC_ATTN_CASE(LPV)                                                                  \
-  if (L <= LPV) return bwd ? launch_bwd<LPV, DK>(p, stream) : launch_fwd<LPV, DK>(p, stream);
+#define LSTC_ATTN_CASE(LPV) \
+  if (L <= LPV) return bwd ? launch<LPV, DK, true>(p, stream) : launch<LPV, DK, false>(p, stream);
   LSTC_ATTN_CASE(16)
   LSTC_ATTN_CASE(32)
   LSTC_ATTN_CASE(48)

@@ -37,32 +37,35 @@ __device__ __forceinline__ void store8(void* base, int64_t off, const float (&f)
   }
 }
 
-// block-wide sum of (a, b); `buf` is a [2][MAX_WARPS][2] smem scratch, `phase` alternates per call
-__device__ __forceinline__ void block_sum2(float& a, float& b, float (*buf)[MAX_WARPS][2], int& phase) {
-  a = warp_sum(a);
-  b = warp_sum(b);
+// block-wide sums of N values at once; `buf` is a [2][MAX_WARPS][N] smem scratch, `phase` alternates per call so a
+// single barrier per reduction suffices
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float (*buf)[MAX_WARPS][N], int& phase) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   if (lane == 0) {
-    buf[phase][warp][0] = a;
-    buf[phase][warp][1] = b;
+#pragma unroll
+    for (int i = 0; i < N; ++i) buf[phase][warp][i] = v[i];
   }
   __syncthreads();
-  float ra = 0.f, rb = 0.f;
-  for (int i = 0; i < nw; ++i) {
-    ra += buf[phase][i][0];
-    rb += buf[phase][i][1];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = 0.f;
+  for (int w = 0; w < nw; ++w) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += buf[phase][w][i];
   }
-  a = ra;
-  b = rb;
   phase ^= 1;
 }
+
+constexpr int RPI = 2;  // rows per CTA iteration: twice the bytes in flight, half the barriers per row
 
 template <int NV, bool X_F32, bool Y_F32>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, void* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int64_t rows, int D, float eps) {
-  __shared__ float buf[2][MAX_WARPS][2];
+  __shared__ float buf[2][MAX_WARPS][RPI];
   int phase = 0;
   const int tid = threadIdx.x;
   float gm[NV][8], bt[NV][8];
@@ -75,49 +78,99 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
     }
   }
   const float invD = 1.0f / (float)D;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    float xv[NV][8];
-    float s = 0.f, dummy = 0.f;
+  for (int64_t row0 = (int64_t)blockIdx.x * RPI; row0 < rows; row0 += (int64_t)gridDim.x * RPI) {
+    float xv[RPI][NV][8];
+    float s[RPI];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-        load8<X_F32>(x, row * D + c, xv[v]);
+    for (int r = 0; r < RPI; ++r) {
+      s[r] = 0.f;
+      if (row0 + r < rows) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += xv[v][j];
-      }
-    }
-    block_sum2(s, dummy, buf, phase);
-    const float mean = s * invD;
-    float q = 0.f;
-    dummy = 0.f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = xv[v][j] - mean;
-          q += d * d;
+        for (int v = 0; v < NV; ++v) {
+          const int c = (v * blockDim.x + tid) * 8;
+          if (c < D) load8<X_F32>(x, (row0 + r) * D + c, xv[r][v]);
         }
       }
     }
-    block_sum2(q, dummy, buf, phase);
-    const float rstd = rsqrtf(q * invD + eps);
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-        float o[8];
+    for (int r = 0; r < RPI; ++r) {
+      if (row0 + r < rows) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (xv[v][j] - mean) * rstd * gm[v][j] + bt[v][j];
-        store8<Y_F32>(y, row * D + c, o);
+        for (int v = 0; v < NV; ++v) {
+          const int c = (v * blockDim.x + tid) * 8;
+          if (c < D) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[r] += xv[r][v][j];
+          }
+        }
       }
     }
-    if (tid == 0) {
-      mean_out[row] = mean;
-      rstd_out[row] = rstd;
+    block_sum_n<RPI>(s, buf, phase);
+    float mean[RPI], q[RPI];
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      mean[r] = s[r] * invD;
+      q[r] = 0.f;
+      if (row0 + r < rows) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = (v * blockDim.x + tid) * 8;
+          if (c < D) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float d = xv[r][v][j] - mean[r];
+              q[r] += d * d;
+            }
+          }
+        }
+      }
     }
+    block_sum_n<RPI>(q, buf, phase);
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      if (row0 + r < rows) {
+        const float rstd = rsqrtf(q[r] * invD + eps);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = (v * blockDim.x + tid) * 8;
+          if (c < D) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (xv[r][v][j] - mean[r]) * rstd * gm[v][j] + bt[v][j];
+            store8<Y_F32>(y, (row0 + r) * D + c, o);
+          }
+        }
+        if (tid == 0) {
+          mean_out[row0 + r] = mean[r];
+          rstd_out[row0 + r] = rstd;
+        }
+      }
+    }
+  }
+}
+
+// raw (still packed) 8-element vector: prefetched one row ahead without paying for unpacked fp32 registers
+template <bool IS_F32>
+struct Raw8 {
+  uint4 a, b;  // bf16: only `a` is used
+};
+template <bool IS_F32>
+__device__ __forceinline__ void load_raw(const void* base, int64_t off, Raw8<IS_F32>& r) {
+  if (IS_F32) {
+    r.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + off));
+    r.b = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + off + 4));
+  } else {
+    r.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+  }
+}
+template <bool IS_F32>
+__device__ __forceinline__ void unpack_raw(const Raw8<IS_F32>& r, float (&f)[8]) {
+  if (IS_F32) {
+    f[0] = __uint_as_float(r.a.x); f[1] = __uint_as_float(r.a.y); f[2] = __uint_as_float(r.a.z);
+    f[3] = __uint_as_float(r.a.w); f[4] = __uint_as_float(r.b.x); f[5] = __uint_as_float(r.b.y);
+    f[6] = __uint_as_float(r.b.z); f[7] = __uint_as_float(r.b.w);
+  } else {
+    unpack8(r.a, f);
   }
 }
 
@@ -126,11 +179,11 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, void* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_drop, float drop_scale, uint32_t drop_thr16, uint64_t seed,
-              uint64_t offset, float* __restrict__ partial /*[grid][2][D]*/, int64_t rows, int D) {
+              uint64_t offset, float* __restrict__ partial /*[grid][3][D]*/, int want_dxsum, int64_t rows, int D) {
   __shared__ float buf[2][MAX_WARPS][2];
   int phase = 0;
   const int tid = threadIdx.x;
-  float gm[NV][8], dg[NV][8], db[NV][8];
+  float gm[NV][8], dg[NV][8], db[NV][8], dxs[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c = (v * blockDim.x + tid) * 8;
@@ -139,35 +192,73 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
     for (int j = 0; j < 8; ++j) {
       dg[v][j] = 0.f;
       db[v][j] = 0.f;
+      dxs[v][j] = 0.f;
     }
   }
   const float invD = 1.0f / (float)D;
   const int64_t ld8 = D >> 3;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
-    float xh[NV][8], dyg[NV][8];
-    float s1 = 0.f, s2 = 0.f;
+  // software pipeline: the (packed) operands of the next row are in flight while this row is reduced
+  Raw8<X_F32> nx[NV];
+  Raw8<DY_F32> ndy[NV];
+  float nmean = 0.f, nrstd = 0.f;
+  int64_t row = blockIdx.x;
+  if (row < rows) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = (v * blockDim.x + tid) * 8;
       if (c < D) {
-        float dyv[8];
-        load8<X_F32>(x, row * D + c, xh[v]);
-        load8<DY_F32>(dy, row * D + c, dyv);
+        load_raw<X_F32>(x, row * D + c, nx[v]);
+        load_raw<DY_F32>(dy, row * D + c, ndy[v]);
+      }
+    }
+    nmean = __ldg(mean_in + row);
+    nrstd = __ldg(rstd_in + row);
+  }
+  for (; row < rows; row += gridDim.x) {
+    float xh[NV][8], dyg[NV][8];
+    const float mean = nmean, rstd = nrstd;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = (v * blockDim.x + tid) * 8;
+      if (c < D) {
+        unpack_raw<X_F32>(nx[v], xh[v]);
+        unpack_raw<DY_F32>(ndy[v], dyg[v]);
+      }
+    }
+    const int64_t nrow = row + gridDim.x;
+    if (nrow < rows) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = (v * blockDim.x + tid) * 8;
+        if (c < D) {
+          load_raw<X_F32>(x, nrow * D + c, nx[v]);
+          load_raw<DY_F32>(dy, nrow * D + c, ndy[v]);
+        }
+      }
+      nmean = __ldg(mean_in + nrow);
+      nrstd = __ldg(rstd_in + nrow);
+    }
+    float red[2] = {0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = (v * blockDim.x + tid) * 8;
+      if (c < D) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[v][j] = (xh[v][j] - mean) * rstd;
-          dg[v][j] += dyv[j] * xh[v][j];
-          db[v][j] += dyv[j];
-          dyg[v][j] = dyv[j] * gm[v][j];
-          s1 += dyg[v][j];
-          s2 += dyg[v][j] * xh[v][j];
+          const float xhat = (xh[v][j] - mean) * rstd;
+          const float d = dyg[v][j];
+          xh[v][j] = xhat;
+          dg[v][j] += d * xhat;
+          db[v][j] += d;
+          const float dgm = d * gm[v][j];
+          dyg[v][j] = dgm;
+          red[0] += dgm;
+          red[1] += dgm * xhat;
         }
       }
     }
-    block_sum2(s1, s2, buf, phase);
-    s1 *= invD;
-    s2 *= invD;
+    block_sum_n<2>(red, buf, phase);
+    const float s1 = red[0] * invD, s2 = red[1] * invD;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = (v * blockDim.x + tid) * 8;
@@ -182,28 +273,51 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
           for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * drop_scale : 0.f;
           store8<false>(dx_drop, row * D + c, o);
         }
+        if (want_dxsum) {
+          // column sums of the gradient that enters the preceding Linear (its bias gradient), taken on the
+          // bf16-rounded values so they equal a column sum of the stored tensor
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dxs[v][j] += (DX_F32 && dx_drop == nullptr) ? o[j] : __bfloat162float(__float2bfloat16(o[j]));
+        }
       }
     }
   }
-  float* pg = partial + (int64_t)blockIdx.x * 2 * D;
+  float* pg = partial + (int64_t)blockIdx.x * 3 * D;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c = (v * blockDim.x + tid) * 8;
     if (c < D) {
       store8<true>(pg, c, dg[v]);
       store8<true>(pg + D, c, db[v]);
+      if (want_dxsum) store8<true>(pg + 2 * D, c, dxs[v]);
     }
   }
 }
 
-// out[k][c] = sum_b partial[b][k][c], k in {0,1}
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int D,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * D) return;
+// out[k][c] = sum_b partial[b][k][c], k in {0,1,(2)}: block (32 columns, 8 partial lanes), coalesced 128-byte reads
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int D, int nk, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dxsum) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;  // column index in [0, nk*D)
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * 2 * D + c];
-  if (c < D) dgamma[c] = s; else dbeta[c - D] = s;
+  if (c < nk * D) {
+    const int k = c / D, col = c - k * D;
+    for (int b = ty; b < nblocks; b += 8) s += partial[((int64_t)b * 3 + k) * D + col];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < nk * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    const int k = c / D, col = c - k * D;
+    if (k == 0) dgamma[col] = t;
+    else if (k == 1) dbeta[col] = t;
+    else dxsum[col] = t;
+  }
 }
 
 static int threads_for(int64_t D, int& nv) {
@@ -216,7 +330,7 @@ static int threads_for(int64_t D, int& nv) {
 }
 
 static int64_t bwd_grid(int64_t rows) {
-  int64_t g = (int64_t)num_sms() * 8;
+  int64_t g = (int64_t)num_sms() * 4;
   if (g > rows) g = rows;
   if (g < 1) g = 1;
   return g;
@@ -238,7 +352,7 @@ extern "C" int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamm
   int nv;
   const int threads = ln::threads_for(D, nv);
   int64_t grid = (int64_t)num_sms() * 8;
-  if (grid > rows) grid = rows;
+  if (grid > (rows + ln::RPI - 1) / ln::RPI) grid = (rows + ln::RPI - 1) / ln::RPI;
 #define LSTC_LN_FWD(NV)                                                                                         \
   do {                                                                                                          \
     if (x_is_f32 && y_is_f32)                                                                                   \
@@ -263,13 +377,13 @@ extern "C" int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamm
 }
 
 extern "C" int64_t lstc_layernorm_bwd_workspace(int64_t rows, int64_t D) {
-  return ln::bwd_grid(rows) * 2 * D * (int64_t)sizeof(float);
+  return ln::bwd_grid(rows) * 3 * D * (int64_t)sizeof(float);
 }
 
 extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, int x_is_f32, const float* gamma,
                                   const float* mean, const float* rstd, void* dx, int dx_is_f32, void* dx_drop,
                                   float drop_p, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,
-                                  void* workspace, int64_t rows, int64_t D, void* stream_) {
+                                  float* dxsum, void* workspace, int64_t rows, int64_t D, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LSTC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace,
                  "lstc_layernorm_bwd: null pointer");
@@ -279,6 +393,7 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
   if (rows == 0) {
     LSTC_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, D * sizeof(float), stream));
     LSTC_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, D * sizeof(float), stream));
+    if (dxsum) LSTC_CHECK_CUDA(cudaMemsetAsync(dxsum, 0, D * sizeof(float), stream));
     return LSTC_OK;
   }
   int nv;
@@ -291,7 +406,7 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
 #define LSTC_LN_BWD_K(NV, A, B, C)                                                                             \
   ln::ln_bwd_kernel<NV, A, B, C><<<(unsigned)grid, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dx, dd,    \
                                                                          dscale, thr, seed, offset, partial,  \
-                                                                         rows, (int)D)
+                                                                         dxsum != nullptr ? 1 : 0, rows, (int)D)
 #define LSTC_LN_BWD(NV)                                             \
   do {                                                              \
     if (dy_is_f32 && x_is_f32 && dx_is_f32) LSTC_LN_BWD_K(NV, true, true, true);         \
@@ -309,8 +424,9 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
 #undef LSTC_LN_BWD
 #undef LSTC_LN_BWD_K
   LSTC_CHECK_LAUNCH();
-  ln::ln_bwd_finalize_kernel<<<(unsigned)((2 * D + 255) / 256), 256, 0, stream>>>(partial, (int)grid, (int)D, dgamma,
-                                                                                dbeta);
+  const int nk = dxsum != nullptr ? 3 : 2;
+  ln::ln_bwd_finalize_kernel<<<(unsigned)((nk * D + 31) / 32), 256, 0, stream>>>(partial, (int)grid, (int)D, nk, dgamma,
+                                                                               dbeta, dxsum);
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }

@@ -325,12 +325,14 @@ class FFNBlockFn(torch.autograd.Function):
         g2 = g.contiguous().view(-1, D)
         dlnw = dlnb = None
         if cfg.layer_norm:
-            gy2, gy2d, dlnw, dlnb = ops.layernorm_bwd(g2, y2, ln_w.detach(), mean, rstd, cfg.drop)
+            # the LayerNorm backward also yields the column sums of the gradient entering w_2 (= d b_2)
+            gy2, gy2d, dlnw, dlnb, db2 = ops.layernorm_bwd(g2, y2, ln_w.detach(), mean, rstd, cfg.drop, want_dxsum=True)
+            gin = gy2d if gy2d is not None else gy2
         else:
             gy2 = g2
             gy2d = ops.dropout_apply(g2, cfg.drop) if cfg.drop[0] > 0 else None
-        gin = gy2d if gy2d is not None else gy2
-        db2 = ops.colsum(gin)
+            gin = gy2d if gy2d is not None else gy2
+            db2 = ops.colsum(gin)
         dw2 = _wgrad(gin, h)                                                  # [D, Dh+pad]
         dh = ops.gemm(gin, CACHE.bf16(w2, pad_cols=pad), b_mn=True, relu_mask=h)   # [M, Dh+pad]
         db1 = ops.colsum(dh)

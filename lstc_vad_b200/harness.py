@@ -405,3 +405,18 @@ def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torc
             vals += [win_scores[(key, wi)]] * cover
         result[key] = torch.tensor(vals, dtype=torch.float32)
     return result
+
+
+def save_pseudo_labels(path: str, scores: Dict[str, torch.Tensor]) -> None:
+    """Writes {key + '.npy': float32 [n_clips, 1]} with np.save — the pickled-dict format the reference's generators
+    produce (Train/pseudo_labels_generator_temporal.py:142-145) and its datasets read back
+    (utils/load_dataset.py:17-25)."""
+    import numpy as np
+    out = {k + ".npy": v.detach().cpu().numpy().astype(np.float32).reshape(-1, 1) for k, v in scores.items()}
+    np.save(path, out)
+
+
+def frame_scores(clip_scores: torch.Tensor, segment_len: int = 16) -> torch.Tensor:
+    """Per-clip scores -> per-frame scores (each clip covers `segment_len` frames), as the evaluation loop does
+    (Test/evaluation_shanghaitech_ubnormal.py:92)."""
+    return clip_scores.repeat_interleave(segment_len)

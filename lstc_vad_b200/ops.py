@@ -226,8 +226,8 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
-                  dropout: Dropout = NO_DROPOUT):
-    """-> (dx [same dtype as x], dx_drop bf16 | None, dgamma, dbeta)."""
+                  dropout: Dropout = NO_DROPOUT, want_dxsum: bool = False):
+    """-> (dx [same dtype as x], dx_drop bf16 | None, dgamma, dbeta[, dxsum if want_dxsum])."""
     lib = _lib.load()
     _cuda(dy, "dy")
     _cuda(x, "x")
@@ -241,11 +241,14 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
     dgamma = torch.empty(D, device=x.device, dtype=F32)
     dbeta = torch.empty(D, device=x.device, dtype=F32)
     ws = torch.empty(max(1, lib.lstc_layernorm_bwd_workspace(rows, D)), device=x.device, dtype=torch.uint8)
+    dxsum = torch.empty(D, device=x.device, dtype=F32) if want_dxsum else None
     st = lib.lstc_layernorm_bwd(_p(dy), int(dy.dtype == F32), _p(x), int(x.dtype == F32), _p(gamma), _p(mean),
                                 _p(rstd), _p(dx), int(dx.dtype == F32), _p(dx_drop), float(p), int(seed), int(off),
-                                _p(dgamma), _p(dbeta), _p(ws), rows, D, _stream())
+                                _p(dgamma), _p(dbeta), _p(dxsum), _p(ws), rows, D, _stream())
     _lib.check(st, "lstc_layernorm_bwd")
     LAUNCHES.add(2)
+    if want_dxsum:
+        return dx, dx_drop, dgamma, dbeta, dxsum
     return dx, dx_drop, dgamma, dbeta
 
 

@@ -32,7 +32,7 @@ def assert_close(name, got, ref, rtol=2e-2, atol=2e-2):
     assert ok, msg
 
 
-def tensor_close(name, got, ref, rel_l2=3e-2, p999=6e-2, max_rel=0.3, floor=1e-6):
+def tensor_close(name, got, ref, rel_l2=6e-2, p999=1e-1, max_rel=0.4, floor=1e-6):
     """Tolerance model for bf16-activation tensors (encoder outputs, gradients), all relative to max|ref|:
          ||got - ref||_F / ||ref||_F <= rel_l2          (bulk error)
          99.9 % of the elements within p999 * max|ref|  (no systematic layout error)

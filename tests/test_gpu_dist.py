@@ -1,0 +1,77 @@
+"""Multi-GPU parity (needs >= 2 GPUs, NCCL): the bag-sharded data-parallel train step (score all-gather, global
+MIL loss, bucketed gradient all-reduce overlapped with backward) reproduces the single-GPU step on the same
+global batch — loss terms and every parameter gradient (dropout off)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _workload():
+    from lstc_vad_b200.harness import Workload
+    return Workload("dp_test", 256, 512, 3, 16, 4, 4, n_layers=2, n_head=2, d_k=64, dropouts=(0, 0, 0, 0))
+
+
+def _global_batch(wl, device):
+    from lstc_vad_b200.harness import synthetic_step_inputs
+    return synthetic_step_inputs(wl, seed=3, batch_size=wl.batch_size, device=device)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from lstc_vad_b200.harness import TrainStep
+    wl = _workload()
+    feats, labs = _global_batch(wl, dev)
+    B, P = wl.batch_size, wl.part_num
+    Bl = B // world
+    nh = B * P
+    sel = torch.cat([torch.arange(rank * Bl * P, (rank + 1) * Bl * P), nh + torch.arange(rank * Bl * P, (rank + 1) * Bl * P)]).to(dev)
+    step = TrainStep(wl, dev, seed=11, train_mode=False, process_group=dist.group.WORLD)
+    for _ in range(2):  # second pass exercises the static bucket plan (unused params dropped after step 1)
+        step.zero_grad()
+        terms = step.forward_backward(feats[sel].contiguous(), labs[sel].contiguous(), Bl)
+    torch.cuda.synchronize()
+    ce = terms["ce"].detach().clone()
+    dist.all_reduce(ce)
+    if rank == 0:
+        grads = {n: p.grad.detach().cpu().clone() for n, p in list(step.encoder.named_parameters()) +
+                 [("head." + n, p) for n, p in step.head.named_parameters()] if p.grad is not None}
+        torch.save(dict(mil=terms["mil"].item(), ce=ce.item(), grads=grads), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_data_parallel_step_equals_single_gpu(tmp_path):
+    from lstc_vad_b200.harness import TrainStep
+    out = str(tmp_path / "dp.pt")
+    port = 29600 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    wl = _workload()
+    feats, labs = _global_batch(wl, dev)
+    ref = TrainStep(wl, dev, seed=11, train_mode=False)
+    ref.zero_grad()
+    terms = ref.forward_backward(feats, labs, wl.batch_size)
+    assert abs(got["mil"] - terms["mil"].item()) < 1e-5   # same scores bit for bit -> same global MIL loss
+    assert abs(got["ce"] - terms["ce"].item()) < 1e-5
+    named = list(ref.encoder.named_parameters()) + [("head." + n, p) for n, p in ref.head.named_parameters()]
+    checked = 0
+    for n, p in named:
+        if p.grad is None:
+            assert n not in got["grads"], n
+            continue
+        g, r = got["grads"][n].float(), p.grad.detach().cpu().float()
+        err = (g - r).norm() / r.norm().clamp_min(1e-12)
+        # identical kernels on the two halves; only the summation order over windows (and split-K atomics) differs
+        assert err < 1e-3, (n, err.item())
+        checked += 1
+    assert checked > 20

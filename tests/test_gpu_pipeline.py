@@ -1,0 +1,185 @@
+"""Pipeline-level parity (GPU): batched, sharded scoring / pseudo-label generation against the reference's
+one-window-per-forward loops (restated with the CPU oracle), frame-level ROC-AUC delta on a fixed synthetic split,
+pseudo-label file format, and a few optimizer steps of the fused train step against torch.optim.Adagrad.
+
+Stated tolerances: |ROC-AUC(cuda) - ROC-AUC(oracle)| <= 1e-3 (north star); per-clip scores max-abs <= 1.5e-2;
+thresholded pseudo labels identical wherever the oracle score is further than 1.5e-2 from the threshold."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(n_layers=2, n_head=2, d_k=64, d_v=64, d_model=128, d_inner=256, MHA_layerNorm=True, FFN_layerNorm=True,
+          weight_init=False, relative_pe=True, window_size=4, window_depth=3)
+D, N, T = 128, 16, 3
+
+
+def make_corpus(n_videos=30, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    videos, frame_labels = {}, {}
+    direction = torch.randn(D, generator=g)
+    for i in range(n_videos):
+        n = int(torch.randint(4, 41, (1,), generator=g))
+        f = torch.randn(n, N, D, generator=g).abs()
+        lab = torch.zeros(n)
+        if i % 2 == 1:  # abnormal video: a contiguous run of clips carries a feature offset
+            a = int(torch.randint(0, n - 1, (1,), generator=g))
+            b = min(n, a + int(torch.randint(2, 12, (1,), generator=g)))
+            f[a:b] += 0.6 * direction.abs()
+            lab[a:b] = 1
+        videos[f"vid_{i:03d}"] = f
+        frame_labels[f"vid_{i:03d}"] = lab.repeat_interleave(16)
+    return videos, frame_labels
+
+
+def trained_state(videos, frame_labels, steps=30):
+    """A few plain-SGD steps on the CPU oracle so the scores separate normal from abnormal clips (deterministic)."""
+    from lstc_vad_b200.models import Classifier, Encoder
+    torch.manual_seed(0)
+    enc, cls = Encoder(**KW), Classifier(D, 0.6)
+    esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    csd = {k: v.clone().requires_grad_(True) for k, v in cls.state_dict().items()}
+    cfg = O.EncoderConfig(**{k: v for k, v in KW.items() if k in O.EncoderConfig.__dataclass_fields__})
+    xs, ys = [], []
+    for k, f in videos.items():
+        for b in range(0, f.shape[0] - T + 1, T):
+            xs.append(f[b:b + T].reshape(T * N, D))
+            ys.append(frame_labels[k][b * 16:(b + T) * 16].mean())
+    x, y = torch.stack(xs), torch.stack(ys)
+    params = [t for t in list(esd.values()) + list(csd.values()) if t.requires_grad]
+    for _ in range(steps):
+        out = O.encoder_forward(esd, x, cfg)
+        p = O.head_forward(csd, out[:, 0, :], "classifier")[:, 1]
+        loss = torch.nn.functional.binary_cross_entropy(p, y)
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        with torch.no_grad():
+            for t, gr in zip(params, grads):
+                if gr is not None:
+                    t -= 0.05 * gr
+    return {k: v.detach() for k, v in esd.items()}, {k: v.detach() for k, v in csd.items()}, cfg
+
+
+def oracle_scores(esd, csd, cfg, videos, backshift, threshold=None):
+    """The reference loops restated: one window per forward (Test/evaluation_shanghaitech_ubnormal.py:69-94 with
+    backshift, Train/pseudo_labels_generator_temporal.py:113-143 without)."""
+    res = {}
+    with torch.no_grad():
+        for k, f in videos.items():
+            n = f.shape[0]
+            vals = []
+            n_win = (n + T - 1) // T
+            for i in range(n_win):
+                beg = i * T
+                end = n if i == n_win - 1 else (i + 1) * T
+                if backshift and end - beg < T and end - T >= 0:
+                    w = f[end - T:end]
+                else:
+                    w = f[beg:end]
+                out = O.encoder_forward(esd, w.reshape(1, -1, D), cfg)
+                sc = O.head_forward(csd, out[:, 0, :], "classifier")[:, 1]
+                if threshold is not None:
+                    sc = O.threshold_labels(sc, threshold)
+                vals += [sc.item()] * (end - beg)
+            res[k] = torch.tensor(vals)
+    return res
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from lstc_vad_b200.models import Classifier, Encoder
+    videos, frame_labels = make_corpus()
+    esd, csd, cfg = trained_state(videos, frame_labels)
+    enc, cls = Encoder(**KW), Classifier(D, 0.6)
+    enc.load_state_dict(esd, strict=True)
+    cls.load_state_dict(csd, strict=True)
+    return videos, frame_labels, esd, csd, cfg, enc.cuda().eval(), cls.cuda().eval()
+
+
+def test_frame_level_auc_delta_against_oracle(setup):
+    from sklearn.metrics import auc, roc_curve
+    from lstc_vad_b200.harness import frame_scores, score_videos
+    videos, frame_labels, esd, csd, cfg, enc, cls = setup
+    ref = oracle_scores(esd, csd, cfg, videos, backshift=True)
+    got = score_videos(enc, cls, videos, part_len=T, backshift=True)
+    keys = sorted(videos)
+    for k in keys:
+        assert got[k].shape == ref[k].shape == (videos[k].shape[0],)
+    diff = max((got[k] - ref[k]).abs().max().item() for k in keys)
+    y = torch.cat([frame_labels[k] for k in keys]).numpy()
+    s_ref = torch.cat([frame_scores(ref[k]) for k in keys]).numpy()
+    s_got = torch.cat([frame_scores(got[k]) for k in keys]).numpy()
+    fpr, tpr, _ = roc_curve(y, s_ref)
+    auc_ref = auc(fpr, tpr)
+    fpr, tpr, _ = roc_curve(y, s_got)
+    auc_got = auc(fpr, tpr)
+    print(f"per-clip score max-abs diff {diff:.3e}; ROC-AUC oracle {auc_ref:.5f} cuda {auc_got:.5f} "
+          f"delta {abs(auc_got - auc_ref):.2e}; score range {s_ref.min():.3f}..{s_ref.max():.3f}")
+    assert diff <= 1.5e-2
+    assert 0.55 < auc_ref < 1.0, "the synthetic split should be informative"
+    assert abs(auc_got - auc_ref) <= 1e-3
+
+
+def test_sharded_pseudo_label_generation_matches_reference_loop(setup, tmp_path):
+    from lstc_vad_b200.harness import save_pseudo_labels, score_videos, shard_videos
+    videos, _, esd, csd, cfg, enc, cls = setup
+    thr = 0.5
+    ref = oracle_scores(esd, csd, cfg, videos, backshift=False, threshold=thr)
+    ref_raw = oracle_scores(esd, csd, cfg, videos, backshift=False)
+    keys = sorted(videos)
+    n_clips = [videos[k].shape[0] for k in keys]
+    merged = {}
+    for rank in range(4):  # 4 "ranks" on one GPU: shards are disjoint, no collective, rank 0 would merge
+        mine = shard_videos(keys, n_clips, 4, rank)
+        part = score_videos(enc, cls, {keys[i]: videos[keys[i]] for i in mine}, part_len=T, backshift=False, threshold=thr)
+        assert not (set(part) & set(merged))
+        merged.update(part)
+    assert sorted(merged) == keys
+    n_checked = 0
+    for k in keys:
+        safe = (ref_raw[k] - thr).abs() > 1.5e-2
+        # bit-level agreement of the keep/zero decision wherever the score is not within noise of the threshold
+        assert torch.equal(merged[k][safe] > 0, ref[k][safe] > 0)
+        assert (merged[k][safe] - ref[k][safe]).abs().max().item() <= 1.5e-2 if safe.any() else True
+        n_checked += int(safe.sum())
+    assert n_checked > 0.8 * sum(n_clips)
+    path = str(tmp_path / "pseudo.npy")
+    save_pseudo_labels(path, merged)
+    loaded = np.load(path, allow_pickle=True).tolist()  # how utils/load_dataset.py:17-25 reads it
+    assert sorted(loaded) == [k + ".npy" for k in keys]
+    v = loaded[keys[0] + ".npy"]
+    assert v.dtype == np.float32 and v.shape == (videos[keys[0]].shape[0], 1)
+
+
+def test_threshold_is_bit_exact_on_identical_scores():
+    from lstc_vad_b200.losses import threshold_pseudo_labels
+    s = torch.rand(4099, device="cuda")
+    s[:5] = 0.65
+    assert torch.equal(threshold_pseudo_labels(s, 0.65).cpu(), O.threshold_labels(s.cpu(), 0.65))
+
+
+def test_train_steps_with_fused_adagrad_track_torch_adagrad():
+    """3 optimizer steps: TrainStep(optimizer=True) (fused Adagrad kernel) vs torch.optim.Adagrad on an identical
+    second copy of the modules, dropout off.  Same gradients (same kernels) -> parameters agree to fp32 rounding."""
+    from lstc_vad_b200.harness import TrainStep, Workload, synthetic_step_inputs
+    wl = Workload("tiny", 128, 256, 3, 16, 4, 2, n_layers=1, n_head=2, d_k=64, dropouts=(0, 0, 0, 0))
+    dev = torch.device("cuda", 0)
+    a = TrainStep(wl, dev, seed=5, train_mode=False, optimizer=True)
+    b = TrainStep(wl, dev, seed=5, train_mode=False, optimizer=False)
+    opt = torch.optim.Adagrad([{"params": b.encoder.parameters(), "lr": 1e-4},
+                               {"params": b.head.parameters(), "lr": 1e-2}], weight_decay=1e-3)
+    for i in range(3):
+        feats, labs = synthetic_step_inputs(wl, seed=i, device=dev)
+        a.zero_grad()
+        ta = a.forward_backward(feats, labs, wl.batch_size)
+        opt.zero_grad()
+        tb = b.forward_backward(feats, labs, wl.batch_size)
+        opt.step()
+        assert abs(ta["loss"].item() - tb["loss"].item()) < 2e-3
+    for (na, pa), (nb, pb) in zip(a.encoder.named_parameters(), b.encoder.named_parameters()):
+        assert na == nb
+        assert torch.allclose(pa, pb, rtol=1e-3, atol=2e-5), na
