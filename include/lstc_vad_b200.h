@@ -180,9 +180,15 @@ int lstc_dropout_mask(uint8_t* mask, int64_t rows, int64_t cols, float p, uint64
 int lstc_scale_by_device_scalar(const float* src, const float* scalar_dev, float* dst, int64_t n, void* stream);
 /* Fused multi-tensor-free Adagrad step on one flat fp32 tensor (torch.optim.Adagrad semantics,
  * Train/temporal_transformer_shanghaitech.py:83-85,142): g += wd * p ; state += g*g ;
- * p -= lr * g / (sqrt(state) + eps). */
+ * p -= lr * g / (sqrt(state) + eps).
+ * grad_scale_dev (nullable) is a device scalar multiplied into grad_scale — the clip coefficient of
+ * torch.nn.utils.clip_grad_norm_ (Train/temporal_transformer_shanghaitech.py:139-141), produced without a host
+ * sync by lstc_sumsq_accumulate (accum += sum x^2, accum zeroed by the caller) and lstc_clip_coef
+ * (coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))). */
+int lstc_sumsq_accumulate(const float* x, int64_t n, float* accum, void* stream);
+int lstc_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream);
 int lstc_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, float lr, float weight_decay,
-                      float eps, float grad_scale, void* stream);
+                      float eps, float grad_scale, const float* grad_scale_dev, void* stream);
 
 #ifdef __cplusplus
 }

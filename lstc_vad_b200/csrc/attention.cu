@@ -179,8 +179,21 @@ __device__ __forceinline__ void softmax_dropout(float (&s)[LP / 8][4], uint32_t 
     for (int n = 0; n < LP / 8; ++n) {
       s[n][2 * r] *= inv;
       s[n][2 * r + 1] *= inv;
-      if (p.drop_p > 0.f && row < p.L && n * 8 < p.L) {
-        const uint32_t k8 = dropout_keep8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), p.drop_thr16);
+    }
+    if (p.drop_p > 0.f) {  // warp-uniform
+      // the 4 lanes of a quad share a row: lane t draws the masks of n-tiles t, t+4, ... and the quad exchanges them
+      constexpr int NK = (LP / 8 + 3) / 4;
+      uint32_t mine[NK];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int n = t + 4 * k;
+        mine[k] = 0xffu;
+        if (n < LP / 8 && row < p.L && n * 8 < p.L)
+          mine[k] = dropout_keep8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), p.drop_thr16);
+      }
+#pragma unroll
+      for (int n = 0; n < LP / 8; ++n) {
+        const uint32_t k8 = __shfl_sync(0xffffffffu, mine[n >> 2], (lane & ~3) | (n & 3));
         const uint32_t two = (k8 >> (2 * t)) & 3u;
         kb = (kb & ~(3u << (2 * n))) | (two << (2 * n));
       }
@@ -207,50 +220,55 @@ struct Ring {
   const Params& p;
   uint32_t base;
   int h;
-  int64_t n_it;        // windows this CTA processes
-  int64_t g_issue;     // next stage to issue
-  int64_t g_total;
+  int64_t n_it;     // windows this CTA processes
+  // producer cursor (next stage to issue) and consumer slot, all maintained incrementally (no div / mod)
+  int64_t w_p;      // window of the next stage to issue
+  int ph_p, c_p;    // its phase / chunk
+  int slot_p, slot_c;
 
   __device__ Ring(const Params& p_, uint32_t base_, int h_) : p(p_), base(base_), h(h_) {
     n_it = (p.W - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
     if (n_it < 0) n_it = 0;
-    g_issue = 0;
-    g_total = n_it * SPW;
+    w_p = blockIdx.x;
+    ph_p = 0; c_p = 0; slot_p = 0; slot_c = NS - 1;  // slot_c is advanced to 0 by the first acquire()
   }
-  __device__ uint32_t tile(int64_t g, int which) const { return base + (uint32_t)(g % NS) * STAGE + which * CT; }
+  __device__ uint32_t cur(int which) const { return base + (uint32_t)slot_c * STAGE + which * CT; }
 
   __device__ void issue_next() {
-    const int64_t g = g_issue++;
-    if (g < g_total) {
-      const int64_t it = g / SPW;
-      const int s = (int)(g % SPW);
-      const int ph = s / NC, c = s % NC;
-      const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
+    if (w_p < p.W) {
       const int HD = p.H * DK;
-      const __nv_bfloat16* q = p.qkv + (w * p.L) * p.ld + h * DK + c * 64;
-      const uint32_t t0 = tile(g, 0), t1 = tile(g, 1);
+      const __nv_bfloat16* q = p.qkv + (w_p * p.L) * p.ld + h * DK + c_p * 64;
+      const uint32_t t0 = base + (uint32_t)slot_p * STAGE, t1 = t0 + CT;
       if (!BWD) {
-        if (ph == 0) {
+        if (ph_p == 0) {
           load_chunk_tile<LP>(t0, q, p.ld, p.L);
           load_chunk_tile<LP>(t1, q + HD, p.ld, p.L);
         } else {
           load_chunk_tile<LP>(t0, q + 2 * HD, p.ld, p.L);
         }
       } else {
-        const __nv_bfloat16* d_o = p.dout + (w * p.L) * p.ld_dout + h * DK + c * 64;
-        if (ph == 0) {
+        const __nv_bfloat16* d_o = p.dout + (w_p * p.L) * p.ld_dout + h * DK + c_p * 64;
+        if (ph_p == 0) {
           load_chunk_tile<LP>(t0, q, p.ld, p.L);
           load_chunk_tile<LP>(t1, q + HD, p.ld, p.L);
-        } else if (ph == 1) {
+        } else if (ph_p == 1) {
           load_chunk_tile<LP>(t0, d_o, p.ld_dout, p.L);
           load_chunk_tile<LP>(t1, q + 2 * HD, p.ld, p.L);
-        } else if (ph == 2) {
+        } else if (ph_p == 2) {
           load_chunk_tile<LP>(t0, q + HD, p.ld, p.L);  // K_c
           load_chunk_tile<LP>(t1, q, p.ld, p.L);       // Q_c
         } else {
           load_chunk_tile<LP>(t0, d_o, p.ld_dout, p.L);
         }
       }
+      if (++c_p == NC) {
+        c_p = 0;
+        if (++ph_p == (BWD ? 4 : 2)) {
+          ph_p = 0;
+          w_p += gridDim.x;
+        }
+      }
+      slot_p = (slot_p + 1 == NS) ? 0 : slot_p + 1;
     }
     cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
   }
@@ -258,10 +276,11 @@ struct Ring {
 #pragma unroll
     for (int i = 0; i < NS - 1; ++i) issue_next();
   }
-  // Makes stage g resident and visible to all warps, then refills the slot consumed one step earlier.
+  // Makes the next stage resident and visible to all warps (-> cur()), then refills the slot consumed one step earlier.
   __device__ void acquire() {
     cp_async_wait<NS - 2>();
     __syncthreads();
+    slot_c = (slot_c + 1 == NS) ? 0 : slot_c + 1;
     issue_next();
   }
 };
@@ -296,7 +315,6 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) 
   const int m0 = warp * 16;
   R ring(p, s0, h);
   ring.prologue();
-  int64_t gi = 0;
   for (int64_t it = 0; it < ring.n_it; ++it) {
     const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
     float s[NT][4];
@@ -306,9 +324,9 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) 
       s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f;
     }
 #pragma unroll 1
-    for (int c = 0; c < R::NC; ++c, ++gi) {
+    for (int c = 0; c < R::NC; ++c) {
       ring.acquire();
-      mma_acc_rows_x_rowsT<LP>(s, ring.tile(gi, 0), ring.tile(gi, 1), m0, lane);
+      mma_acc_rows_x_rowsT<LP>(s, ring.cur(0), ring.cur(1), m0, lane);
     }
     softmax_dropout<LP>(s, keep, p, w, h, m0, lane);
 #pragma unroll
@@ -337,10 +355,10 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) 
     }
     __nv_bfloat16* obase = p.out + (w * p.L) * p.ld_out + h * DK;
 #pragma unroll 1
-    for (int c = 0; c < R::NC; ++c, ++gi) {
+    for (int c = 0; c < R::NC; ++c) {
       ring.acquire();
       float o[8][4];
-      mma_frag_x_rows<KT>(o, pa, ring.tile(gi, 0), lane);
+      mma_frag_x_rows<KT>(o, pa, ring.cur(0), lane);
       store_chunk(o, 1.0f, obase + c * 64, p.ld_out, m0, p.L, lane);
     }
   }
@@ -372,7 +390,6 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
   }
   R ring(p, s0, h);
   ring.prologue();
-  int64_t gi = 0;
   for (int64_t it = 0; it < ring.n_it; ++it) {
     const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
     {
@@ -385,14 +402,14 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
         dp[n][0] = 0.f; dp[n][1] = 0.f; dp[n][2] = 0.f; dp[n][3] = 0.f;
       }
 #pragma unroll 1
-      for (int c = 0; c < R::NC; ++c, ++gi) {
+      for (int c = 0; c < R::NC; ++c) {
         ring.acquire();
-        mma_acc_rows_x_rowsT<LP>(s, ring.tile(gi, 0), ring.tile(gi, 1), m0, lane);
+        mma_acc_rows_x_rowsT<LP>(s, ring.cur(0), ring.cur(1), m0, lane);
       }
 #pragma unroll 1
-      for (int c = 0; c < R::NC; ++c, ++gi) {
+      for (int c = 0; c < R::NC; ++c) {
         ring.acquire();
-        mma_acc_rows_x_rowsT<LP>(dp, ring.tile(gi, 0), ring.tile(gi, 1), m0, lane);
+        mma_acc_rows_x_rowsT<LP>(dp, ring.cur(0), ring.cur(1), m0, lane);
       }
       softmax_dropout<LP>(s, keep, p, w, h, m0, lane);  // s = P, keep = dropout mask bits
       // dropout backward + softmax backward:  dS = P * (dP - sum_j P dP)
@@ -443,7 +460,7 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
     {
       uint32_t a_ds[KT][4], a_dst[KT][4];
 #pragma unroll 1
-      for (int c = 0; c < R::NC; ++c, ++gi) {
+      for (int c = 0; c < R::NC; ++c) {
         ring.acquire();  // its barrier also publishes Pd / dS of every warp
         if (c == 0) {
 #pragma unroll
@@ -455,9 +472,9 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
           }
         }
         float acc[8][4];
-        mma_frag_x_rows<KT>(acc, a_ds, ring.tile(gi, 0), lane);   // dQ_c = scale * dS K_c
+        mma_frag_x_rows<KT>(acc, a_ds, ring.cur(0), lane);   // dQ_c = scale * dS K_c
         store_chunk(acc, p.scale, dq_base + c * 64, p.ld_out, m0, p.L, lane);
-        mma_frag_x_rows<KT>(acc, a_dst, ring.tile(gi, 1), lane);  // dK_c = scale * dS^T Q_c
+        mma_frag_x_rows<KT>(acc, a_dst, ring.cur(1), lane);  // dK_c = scale * dS^T Q_c
         store_chunk(acc, p.scale, dk_base + c * 64, p.ld_out, m0, p.L, lane);
       }
     }
@@ -467,10 +484,10 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
       for (int i = 0; i < KT; ++i)
         ldsm_x4_t(sPd + (i * 16 + (lane & 7) + (lane >> 4) * 8) * PP + (m0 + ((lane >> 3) & 1) * 8) * 2, a_pdt[i]);
 #pragma unroll 1
-      for (int c = 0; c < R::NC; ++c, ++gi) {
+      for (int c = 0; c < R::NC; ++c) {
         ring.acquire();
         float acc[8][4];
-        mma_frag_x_rows<KT>(acc, a_pdt, ring.tile(gi, 0), lane);  // dV_c = Pd^T dO_c
+        mma_frag_x_rows<KT>(acc, a_pdt, ring.cur(0), lane);  // dV_c = Pd^T dO_c
         store_chunk(acc, 1.0f, dv_base + c * 64, p.ld_out, m0, p.L, lane);
       }
     }

@@ -255,9 +255,32 @@ __global__ void threshold_kernel(const float* __restrict__ s, float thr, float* 
     out[i] = v > thr ? v : 0.f;
   }
 }
+// sum of squares, block-reduced then one atomic per CTA (gradient-norm clipping)
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ accum) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(accum, s);
+  }
+}
+// coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef) {
+  const float c = max_norm / (sqrtf(sumsq[0]) + 1e-6f);
+  coef[0] = c < 1.f ? c : 1.f;
+}
 // torch.optim.Adagrad (lr_decay = 0): g = grad*grad_scale + wd*p ; sum += g*g ; p -= lr * g / (sqrt(sum)+eps)
 __global__ void adagrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ st, int64_t n,
-                               float lr, float wd, float eps, float gscale) {
+                               float lr, float wd, float eps, float gscale_host, const float* __restrict__ gscale_dev) {
+  const float gscale = gscale_host * (gscale_dev != nullptr ? __ldg(gscale_dev) : 1.f);
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -430,14 +453,28 @@ extern "C" int lstc_threshold_labels(const float* scores, float thr, float* out,
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
+extern "C" int lstc_sumsq_accumulate(const float* x, int64_t n, float* accum, void* stream) {
+  LSTC_CHECK_ARG(accum && (n == 0 || x), "lstc_sumsq_accumulate: null pointer");
+  if (n == 0) return LSTC_OK;
+  ew::sumsq_kernel<<<ew::grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, n, accum);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream) {
+  LSTC_CHECK_ARG(sumsq && coef, "lstc_clip_coef: null pointer");
+  ew::clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, coef);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
 extern "C" int lstc_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, float lr,
-                                 float weight_decay, float eps, float grad_scale, void* stream) {
+                                 float weight_decay, float eps, float grad_scale, const float* grad_scale_dev,
+                                 void* stream) {
   LSTC_CHECK_ARG(n == 0 || (param && grad && state_sum), "lstc_adagrad_step: null pointer");
   LSTC_CHECK_ARG(((uintptr_t)param % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)state_sum % 16 == 0),
                  "lstc_adagrad_step: 16-byte alignment");
   if (n == 0) return LSTC_OK;
-  ew::adagrad_kernel<<<ew::grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, state_sum, n, lr,
-                                                                                      weight_decay, eps, grad_scale);
+  ew::adagrad_kernel<<<ew::grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, state_sum, n, lr, weight_decay, eps, grad_scale, grad_scale_dev);
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }

@@ -329,9 +329,21 @@ static int threads_for(int64_t D, int& nv) {
   return threads;
 }
 
-static int64_t bwd_grid(int64_t rows) {
-  int64_t g = (int64_t)num_sms() * 4;
+// persistent grids are sized to exactly one resident wave (SMs x occupancy): a partial second wave would run at a
+// fraction of the occupancy.  The backward partial buffer is sized for the upper bound (8 CTAs / SM).
+static int64_t bwd_grid_max(int64_t rows) {
+  int64_t g = (int64_t)num_sms() * 8;
   if (g > rows) g = rows;
+  if (g < 1) g = 1;
+  return g;
+}
+template <typename K>
+static int64_t resident_grid(K kern, int threads, int64_t work, int cap_per_sm) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+  if (occ > cap_per_sm) occ = cap_per_sm;
+  int64_t g = (int64_t)num_sms() * occ;
+  if (g > work) g = work;
   if (g < 1) g = 1;
   return g;
 }
@@ -351,33 +363,31 @@ extern "C" int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamm
   if (rows == 0) return LSTC_OK;
   int nv;
   const int threads = ln::threads_for(D, nv);
-  int64_t grid = (int64_t)num_sms() * 8;
-  if (grid > (rows + ln::RPI - 1) / ln::RPI) grid = (rows + ln::RPI - 1) / ln::RPI;
-#define LSTC_LN_FWD(NV)                                                                                         \
-  do {                                                                                                          \
-    if (x_is_f32 && y_is_f32)                                                                                   \
-      ln::ln_fwd_kernel<NV, true, true><<<(unsigned)grid, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, \
-                                                                                 rows, (int)D, eps);           \
-    else if (x_is_f32)                                                                                          \
-      ln::ln_fwd_kernel<NV, true, false><<<(unsigned)grid, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, \
-                                                                                  rows, (int)D, eps);          \
-    else if (y_is_f32)                                                                                          \
-      ln::ln_fwd_kernel<NV, false, true><<<(unsigned)grid, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, \
-                                                                                  rows, (int)D, eps);          \
-    else                                                                                                        \
-      ln::ln_fwd_kernel<NV, false, false><<<(unsigned)grid, threads, 0, stream>>>(x, gamma, beta, y, mean,     \
-                                                                                   rstd, rows, (int)D, eps);   \
+  const int64_t iters = (rows + ln::RPI - 1) / ln::RPI;
+#define LSTC_LN_FWD_K(NV, A, B)                                                                       \
+  do {                                                                                                \
+    auto kern = ln::ln_fwd_kernel<NV, A, B>;                                                          \
+    const int64_t grid = ln::resident_grid(kern, threads, iters, 8);                                  \
+    kern<<<(unsigned)grid, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, (int)D, eps);   \
+  } while (0)
+#define LSTC_LN_FWD(NV)                                         \
+  do {                                                          \
+    if (x_is_f32 && y_is_f32) LSTC_LN_FWD_K(NV, true, true);    \
+    else if (x_is_f32) LSTC_LN_FWD_K(NV, true, false);          \
+    else if (y_is_f32) LSTC_LN_FWD_K(NV, false, true);          \
+    else LSTC_LN_FWD_K(NV, false, false);                       \
   } while (0)
   if (nv == 1) LSTC_LN_FWD(1);
   else if (nv == 2) LSTC_LN_FWD(2);
   else LSTC_LN_FWD(4);
 #undef LSTC_LN_FWD
+#undef LSTC_LN_FWD_K
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
 
 extern "C" int64_t lstc_layernorm_bwd_workspace(int64_t rows, int64_t D) {
-  return ln::bwd_grid(rows) * 3 * D * (int64_t)sizeof(float);
+  return ln::bwd_grid_max(rows) * 3 * D * (int64_t)sizeof(float);
 }
 
 extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, int x_is_f32, const float* gamma,
@@ -398,15 +408,18 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
   }
   int nv;
   const int threads = ln::threads_for(D, nv);
-  const int64_t grid = ln::bwd_grid(rows);
+  int64_t grid = 1;
   __nv_bfloat16* dd = (drop_p > 0.f) ? (__nv_bfloat16*)dx_drop : nullptr;
   const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const uint32_t thr = dropout_threshold16(drop_p);
   float* partial = (float*)workspace;
 #define LSTC_LN_BWD_K(NV, A, B, C)                                                                             \
-  ln::ln_bwd_kernel<NV, A, B, C><<<(unsigned)grid, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dx, dd,    \
-                                                                         dscale, thr, seed, offset, partial,  \
-                                                                         dxsum != nullptr ? 1 : 0, rows, (int)D)
+  do {                                                                                                         \
+    auto kern = ln::ln_bwd_kernel<NV, A, B, C>;                                                                \
+    grid = ln::resident_grid(kern, threads, rows, 8);                                                          \
+    kern<<<(unsigned)grid, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dx, dd, dscale, thr, seed, offset,  \
+                                                 partial, dxsum != nullptr ? 1 : 0, rows, (int)D);             \
+  } while (0)
 #define LSTC_LN_BWD(NV)                                             \
   do {                                                              \
     if (dy_is_f32 && x_is_f32 && dx_is_f32) LSTC_LN_BWD_K(NV, true, true, true);         \

@@ -114,7 +114,7 @@ class TrainStep:
     def __init__(self, wl: Workload, device: torch.device, seed: int = 0, train_mode: bool = True,
                  lambda_1: float = 0.01, lambda_MIL: float = 1.0, lambda_CE: float = 0.8,
                  process_group=None, optimizer: bool = False, lr_encoder: float = 1e-4, lr_head: float = 1e-2,
-                 weight_decay: float = 1e-3):
+                 weight_decay: float = 1e-3, clip_grad_norm: Optional[float] = None):
         self.wl, self.device = wl, device
         self.lambda_1, self.lambda_MIL, self.lambda_CE = lambda_1, lambda_MIL, lambda_CE
         self.pg = process_group
@@ -136,7 +136,8 @@ class TrainStep:
         self.opt = None
         if optimizer:
             self.opt = FusedAdagrad([(list(self.encoder.parameters()), lr_encoder),
-                                     (list(self.head.parameters()), lr_head)], weight_decay)
+                                     (list(self.head.parameters()), lr_head)], weight_decay,
+                                    clip_grad_norm=clip_grad_norm)
 
     def parameters(self):
         return list(self.encoder.parameters()) + list(self.head.parameters())
@@ -319,20 +320,21 @@ class FusedAdagrad:
     """torch.optim.Adagrad(lr per group, weight_decay) semantics (Train/temporal_transformer_shanghaitech.py:83-85)
     with one fused kernel per parameter: 5 HBM passes (read grad/param/state, write param/state)."""
 
-    def __init__(self, groups, weight_decay: float, eps: float = 1e-10):
+    def __init__(self, groups, weight_decay: float, eps: float = 1e-10, clip_grad_norm: Optional[float] = None):
         self.groups = groups
         self.wd, self.eps = weight_decay, eps
+        self.clip = clip_grad_norm  # per group, like the scripts' per-model clip_grad_norm_(.., 10)
         self.state: Dict[int, torch.Tensor] = {}
 
     def step(self):
         for params, lr in self.groups:
-            for p in params:
-                if p.grad is None:
-                    continue
+            live = [p for p in params if p.grad is not None]
+            coef = ops.grad_clip_coef([p.grad for p in live], self.clip) if (self.clip and live) else None
+            for p in live:
                 st = self.state.get(id(p))
                 if st is None:
                     st = self.state[id(p)] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                ops.adagrad_step(p.data, p.grad.contiguous(), st, lr, self.wd, self.eps)
+                ops.adagrad_step(p.data, p.grad.contiguous(), st, lr, self.wd, self.eps, 1.0, coef)
         Fn.invalidate_weight_cache()  # parameters were updated through raw pointers
 
 

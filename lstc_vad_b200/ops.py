@@ -492,14 +492,32 @@ def scale_by_device_scalar(src: torch.Tensor, scalar: torch.Tensor) -> torch.Ten
     return dst
 
 
+def grad_clip_coef(grads, max_norm: float) -> torch.Tensor:
+    """Device scalar min(1, max_norm / (||grads||_2 + 1e-6)) over a list of fp32 tensors — clip_grad_norm_ without a
+    host sync (the coefficient is consumed by adagrad_step)."""
+    lib = _lib.load()
+    dev = grads[0].device
+    acc = torch.zeros(2, device=dev, dtype=F32)
+    for g in grads:
+        _cuda(g, "grad", F32)
+        g = g.contiguous()
+        st = lib.lstc_sumsq_accumulate(_p(g), g.numel(), _p(acc), _stream())
+        _lib.check(st, "lstc_sumsq_accumulate")
+        LAUNCHES.add(1)
+    st = lib.lstc_clip_coef(_p(acc), float(max_norm), acc.data_ptr() + 4, _stream())
+    _lib.check(st, "lstc_clip_coef")
+    LAUNCHES.add(1)
+    return acc[1:2]
+
+
 def adagrad_step(param: torch.Tensor, grad: torch.Tensor, state_sum: torch.Tensor, lr: float, weight_decay: float,
-                 eps: float = 1e-10, grad_scale: float = 1.0) -> None:
+                 eps: float = 1e-10, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None) -> None:
     lib = _lib.load()
     for nm, t in (("param", param), ("grad", grad), ("state_sum", state_sum)):
         _cuda(t, nm, F32)
         if not t.is_contiguous():
             raise RuntimeError(f"lstc_vad_b200.adagrad_step: `{nm}` must be contiguous")
     st = lib.lstc_adagrad_step(_p(param), _p(grad), _p(state_sum), param.numel(), float(lr), float(weight_decay),
-                               float(eps), float(grad_scale), _stream())
+                               float(eps), float(grad_scale), _p(grad_scale_dev), _stream())
     _lib.check(st, "lstc_adagrad_step")
     LAUNCHES.add(1)

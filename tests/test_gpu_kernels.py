@@ -338,6 +338,12 @@ def test_adagrad_matches_torch(ops):
         opt.step()
         ops.adagrad_step(p, g, st, lr=1e-2, weight_decay=1e-3, eps=1e-10)
     assert_close("adagrad", p, pr.detach(), rtol=1e-5, atol=1e-6)
+    # gradient-norm clipping coefficient, no host sync
+    gs = [_rand((1000,), 3.0, 60, F32), _rand((77, 5), 3.0, 61, F32)]
+    coef = ops.grad_clip_coef(gs, 10.0)
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in gs)).item()
+    assert abs(coef.item() - min(1.0, 10.0 / (total + 1e-6))) < 1e-6
+    assert ops.grad_clip_coef(gs, 1e9).item() == 1.0
 
 
 # ------------------------------------------------------------------------------------------ heads

@@ -13,7 +13,7 @@ statistics.  Calibration: the REFERENCE ITSELF under torch.autocast(bfloat16) vs
   gradients (parameters and input; they cross up to 3 layers of bf16 backward): relative Frobenius error
                            <= 2e-1 (cosine >= 0.98; the reference's own autocast floor reaches 1.7e-1), 99.9 % within
                            0.3 * max|ref|, every element within 1.0 * max|ref| (one ReLU unit flipping on a 16-window
-                           batch moves a whole weight row); tightened to 1e-1 / 0.15 / 0.5 on the 64-window case
+                           batch moves a whole weight row); tightened to 1.2e-1 / 0.15 / 0.5 on the 64-window case
   top-k indices / thresholded labels: bit-exact whenever the selected scores are separated by > 3e-2.
 """
 import types
@@ -30,7 +30,7 @@ GOLD = Path(__file__).resolve().parent / "golden"
 
 def rel_close(name, got, ref, rel=None, floor=1e-6):
     if "grad" in name and "_64w" in name:  # larger batch: ReLU-flip noise averages out
-        tensor_close(name, got, ref, rel_l2=1e-1, p999=0.15, max_rel=0.5, floor=floor)
+        tensor_close(name, got, ref, rel_l2=1.2e-1, p999=0.15, max_rel=0.5, floor=floor)
     elif "grad" in name:  # gradients have crossed up to 3 layers of bf16 backward: bounded by the autocast floor
         tensor_close(name, got, ref, rel_l2=2e-1, p999=0.3, max_rel=1.0, floor=floor)
     else:
