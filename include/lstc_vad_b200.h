@@ -70,6 +70,24 @@ int lstc_attn_bwd(const void* qkv, int64_t ld, const void* dout, int64_t ld_dout
                   const float* bias, float scale, float dropout_p, uint64_t seed, uint64_t offset, void* dqkv,
                   int64_t ld_dqkv, float* dbias, void* stream);
 
+/* CLS-query attention of the LAST encoder layer (opt-in fast path, `Encoder.forward_cls`): every reference caller
+ * consumes only `feats[:, 0, :]` (Train/temporal_transformer_shanghaitech.py:123), so in the last layer only the
+ * CLS query attends: o = softmax(q_cls K^T * scale) V per (window, head); the CLS row of the rel-pos bias is zero
+ * (models/MultiHeadAttention.py:111).  Exact dead-work elimination of models/MultiHeadAttention.py:103-122.
+ *   q   : bf16 [W, ld_q] (head h at cols h*dk) ; k, v : bf16 [W*L, ld_kv] ; out : bf16 [W, ld_out]
+ * The dropout mask is the row-0 slice of the mask lstc_attn_fwd draws for the same (seed, offset).
+ * Backward: dout bf16 [W, ld_do] -> dq bf16 [W, ld_dq], dk / dv bf16 [W*L, ld_dkv] (every key / value row). */
+int lstc_attn_cls_fwd(const void* q, int64_t ld_q, const void* k, const void* v, int64_t ld_kv, int64_t W, int L,
+                      int H, int dk, float scale, float dropout_p, uint64_t seed, uint64_t offset, void* out,
+                      int64_t ld_out, void* stream);
+int lstc_attn_cls_bwd(const void* q, int64_t ld_q, const void* k, const void* v, int64_t ld_kv, const void* dout,
+                      int64_t ld_do, int64_t W, int L, int H, int dk, float scale, float dropout_p, uint64_t seed,
+                      uint64_t offset, void* dq, int64_t ld_dq, void* dk_out, void* dv_out, int64_t ld_dkv,
+                      void* stream);
+/* dst[r, c] += src[r, c] on bf16 row-strided views (cols, lds multiples of 8) */
+int lstc_add_rows_bf16(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, int64_t rows, int64_t cols,
+                       void* stream);
+
 /* Relative-position bias: dense[h,i,j] = (i>0 && j>0) ? table[index[(i-1)*index_ld + (j-1)], h] : 0
  * (models/MultiHeadAttention.py:107-117; index is the int64 `relative_position_index` buffer, table is
  * `relative_position_bias_table` [T,H]).  The scatter is its transpose: dtable is zero-filled then

@@ -26,6 +26,9 @@ SIGNATURES: dict[str, tuple] = {
                             _I, _I, _P]),
     "lstc_attn_fwd": (_I, [_P, _L, _L, _I, _I, _I, _P, _F, _F, _U, _U, _P, _L, _P, _P]),
     "lstc_attn_bwd": (_I, [_P, _L, _P, _L, _L, _I, _I, _I, _P, _F, _F, _U, _U, _P, _L, _P, _P]),
+    "lstc_attn_cls_fwd": (_I, [_P, _L, _P, _P, _L, _L, _I, _I, _I, _F, _F, _U, _U, _P, _L, _P]),
+    "lstc_attn_cls_bwd": (_I, [_P, _L, _P, _P, _L, _P, _L, _L, _I, _I, _I, _F, _F, _U, _U, _P, _L, _P, _P, _L, _P]),
+    "lstc_add_rows_bf16": (_I, [_P, _L, _P, _L, _L, _L, _P]),
     "lstc_relbias_gather": (_I, [_P, _P, _L, _I, _I, _L, _P, _P]),
     "lstc_relbias_scatter": (_I, [_P, _P, _L, _I, _I, _L, _P, _P]),
     "lstc_layernorm_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _L, _L, _F, _P]),

@@ -19,7 +19,7 @@ OUT_DIR = PKG_DIR / "_C"
 LIB_PATH = OUT_DIR / "liblstc_vad_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "layernorm.cu", "elementwise.cu", "heads.cu", "loss.cu"]
+SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_cls.cu", "layernorm.cu", "elementwise.cu", "heads.cu", "loss.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -286,6 +286,71 @@ class MHABlockFn(torch.autograd.Function):
         return (gx, dwqkv[:HD], dwqkv[HD:2 * HD], dwqkv[2 * HD:], dwfc, dlnw, dlnb, dtable, None, None)
 
 
+class MHAClsFn(torch.autograd.Function):
+    """Last-layer self-attention block restricted to the CLS query (opt-in fast path, exact dead-work elimination):
+    x bf16 [W,L,D] -> out bf16 [W,D] = row 0 of what MHABlockFn would return.  K and V are still projected for every
+    token; Q, the attention, the out-projection, the residual and the LayerNorm run on the W CLS rows only."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, wfc, ln_w, ln_b, table, cfg: MHAConfig):
+        W, L, D = x.shape
+        H, dk = cfg.n_head, cfg.d_k
+        HD = H * dk
+        x = x.contiguous()
+        x2 = x.view(W * L, D)
+        xc = x.view(W, L * D)[:, :D]                      # CLS rows, row pitch L*D
+        ctx.table_shape = None if table is None else tuple(table.shape)
+        wqkv = CACHE.qkv(wq, wk, wv)
+        kv = ops.gemm(x2, wqkv[HD:])                      # [M, 2HD]
+        qc = ops.gemm(xc, wqkv[:HD])                      # [W, HD]
+        scale = 1.0 / (dk ** 0.5)
+        oc = ops.attn_cls_fwd(qc, kv, W, L, H, dk, scale, cfg.attn_drop)
+        y1 = ops.gemm(oc, CACHE.bf16(wfc), residual=xc, dropout=cfg.fc_drop)      # [W, D]
+        if cfg.layer_norm:
+            out, mean, rstd = ops.layernorm_fwd(y1, ln_w.detach(), ln_b.detach(), 1e-6, BF16)
+        else:
+            out, mean, rstd = y1, None, None
+        ctx.cfg, ctx.dims, ctx.scale = cfg, (W, L, D), scale
+        ctx.save_for_backward(x, kv, qc, oc, y1 if cfg.layer_norm else None, mean, rstd, wq, wk, wv, wfc, ln_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, kv, qc, oc, y1, mean, rstd, wq, wk, wv, wfc, ln_w = ctx.saved_tensors
+        cfg: MHAConfig = ctx.cfg
+        W, L, D = ctx.dims
+        H, dk = cfg.n_head, cfg.d_k
+        HD = H * dk
+        x2 = x.view(W * L, D)
+        xc = x.view(W, L * D)[:, :D]
+        g2 = g.contiguous().view(W, D)
+        dlnw = dlnb = None
+        if cfg.layer_norm:
+            gy1, gy1d, dlnw, dlnb = ops.layernorm_bwd(g2, y1, ln_w.detach(), mean, rstd, cfg.fc_drop)
+        else:
+            gy1 = g2
+            gy1d = ops.dropout_apply(g2, cfg.fc_drop) if cfg.fc_drop[0] > 0 else None
+        gfc = gy1d if gy1d is not None else gy1
+        dwfc = _wgrad(gfc, oc)
+        doc = ops.gemm(gfc, CACHE.bf16(wfc), b_mn=True)                          # [W, HD]
+        dqc, dkv = ops.attn_cls_bwd(qc, kv, doc, W, L, H, dk, ctx.scale, cfg.attn_drop)
+        dwq = _wgrad(dqc, xc)                                                    # [HD, D]
+        dwkv = _wgrad(dkv, x2)                                                   # [2HD, D]
+        gx = None
+        if ctx.needs_input_grad[0]:
+            wqkv = CACHE.qkv(wq, wk, wv)
+            gx = ops.gemm(dkv, wqkv[HD:], b_mn=True)                             # [M, D]
+            gcls = ops.gemm(dqc, wqkv[:HD], b_mn=True, residual=gy1)             # [W, D]: query + residual paths
+            ops.add_rows_(gx.view(W, L * D)[:, :D], gcls)
+            gx = gx.view(W, L, D)
+        # the CLS row of the bias is zero, so the table's gradient is exactly zero here — returned as zeros (not None)
+        # because the reference's autograd yields zeros and Adagrad's weight decay still touches the parameter
+        dtable = None
+        if ctx.table_shape is not None and ctx.needs_input_grad[7]:
+            dtable = torch.zeros(ctx.table_shape, device=g.device, dtype=F32)
+        return gx, dwq, dwkv[:HD], dwkv[HD:], dwfc, dlnw, dlnb, dtable, None
+
+
 @dataclass
 class FFNConfig:
     layer_norm: bool

@@ -114,9 +114,10 @@ class TrainStep:
     def __init__(self, wl: Workload, device: torch.device, seed: int = 0, train_mode: bool = True,
                  lambda_1: float = 0.01, lambda_MIL: float = 1.0, lambda_CE: float = 0.8,
                  process_group=None, optimizer: bool = False, lr_encoder: float = 1e-4, lr_head: float = 1e-2,
-                 weight_decay: float = 1e-3, clip_grad_norm: Optional[float] = None):
+                 weight_decay: float = 1e-3, clip_grad_norm: Optional[float] = None, cls_fast_path: bool = False):
         self.wl, self.device = wl, device
         self.lambda_1, self.lambda_MIL, self.lambda_CE = lambda_1, lambda_MIL, lambda_CE
+        self.cls_fast_path = cls_fast_path  # Encoder.forward_cls: skips the last layer's dead (non-CLS) work
         self.pg = process_group
         self.world = 1
         self.rank = 0
@@ -154,8 +155,11 @@ class TrainStep:
         args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=T, lambda_1=self.lambda_1)
         if self.reducer is not None:
             self.reducer.start()
-        out = self.encoder(feats)
-        cls_rows = out[:, 0, :]
+        if self.cls_fast_path:
+            cls_rows = self.encoder.forward_cls(feats)
+        else:
+            out = self.encoder(feats)
+            cls_rows = out[:, 0, :]
         if wl.kind == "ltn":
             probs = self.head(cls_rows.view(2 * B, P, wl.d_model)).view(2 * B * P, -1)
             score = probs[:, 1]
@@ -373,7 +377,7 @@ def shard_videos(keys: Sequence[str], n_clips: Sequence[int], world: int, rank: 
 @torch.no_grad()
 def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torch.Tensor], part_len: int,
                  backshift: bool = False, threshold: Optional[float] = None, max_windows: int = 4096,
-                 n_patch: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                 n_patch: Optional[int] = None, cls_fast_path: bool = False) -> Dict[str, torch.Tensor]:
     """Per-clip scores for every video of this rank's shard: {key: fp32 [n_clips]} on the CPU.
 
     Windows of equal token count from ALL videos are batched into a few large forward calls instead of the
@@ -392,8 +396,8 @@ def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torc
         for s in range(0, len(items), max_windows):
             chunk = items[s:s + max_windows]
             batch = torch.stack([videos[k][b:e, :n_patch].reshape(-1, videos[k].shape[-1]) for k, _, b, e, _ in chunk])
-            out = encoder(batch.to(dev, non_blocking=True).float())
-            sc = head(out[:, 0, :])
+            xin = batch.to(dev, non_blocking=True).float()
+            sc = head(encoder.forward_cls(xin) if cls_fast_path else encoder(xin)[:, 0, :])
             sc = sc[:, 1] if is_cls else sc[:, 0]
             if threshold is not None:
                 sc = losses.threshold_pseudo_labels(sc, threshold)

@@ -46,12 +46,7 @@ class Encoder(nn.Module):
     def _reset_parameters(self):
         xavier_reset(self)
 
-    def forward(self, enc_output, src_mask=None, return_attn=False, return_attn_v=False):
-        require_cuda(enc_output, "Encoder")
-        if src_mask is not None:
-            raise NotImplementedError("attention masks are not supported (no reference caller passes one)")
-        if enc_output.dim() != 3:
-            raise RuntimeError(f"Encoder expects [windows, tokens, d_model], got {tuple(enc_output.shape)}")
+    def _embed(self, enc_output):
         in_dtype = enc_output.dtype
         x = enc_output if in_dtype in (torch.float32, BF16) else enc_output.float()
         if self.input_layerNorm == True:  # noqa: E712
@@ -61,7 +56,33 @@ class Encoder(nn.Module):
         if self.position_encoding == True:  # noqa: E712
             pos = self.position_enc
             drop = Fn.next_dropout(self.position_dropout.p, self.training)
-        x = Fn.ClsPrependFn.apply(x, self.cls_token if self.CLS_learned == True else None, pos, drop)  # noqa: E712
+        return Fn.ClsPrependFn.apply(x, self.cls_token if self.CLS_learned == True else None, pos, drop)  # noqa: E712
+
+    def forward_cls(self, enc_output):
+        """Opt-in fast path (NOT part of the reference API): returns `self.forward(enc_output)[:, 0, :]` — the only
+        part of the output any reference caller consumes — without computing the last layer's out-projection / FFN /
+        LayerNorms and Q projection on the other L-1 tokens (exact dead-work elimination, ~25 % of the FLOPs at L=49).
+        [W, L0, D] -> [W, D] in the caller's dtype."""
+        require_cuda(enc_output, "Encoder")
+        if enc_output.dim() != 3:
+            raise RuntimeError(f"Encoder expects [windows, tokens, d_model], got {tuple(enc_output.shape)}")
+        x = self._embed(enc_output)
+        n = len(self.layer_stack)
+        for i, enc_layer in enumerate(self.layer_stack):
+            if i < n - 1:
+                x, _, _ = enc_layer._forward_bf16(x)
+            else:
+                x = enc_layer._forward_cls_bf16(x)
+        return like_input(x, BF16 if enc_output.dtype == BF16 else torch.float32)
+
+    def forward(self, enc_output, src_mask=None, return_attn=False, return_attn_v=False):
+        require_cuda(enc_output, "Encoder")
+        if src_mask is not None:
+            raise NotImplementedError("attention masks are not supported (no reference caller passes one)")
+        if enc_output.dim() != 3:
+            raise RuntimeError(f"Encoder expects [windows, tokens, d_model], got {tuple(enc_output.shape)}")
+        in_dtype = enc_output.dtype
+        x = self._embed(enc_output)
 
         attn_list, v_list = [], []
         for enc_layer in self.layer_stack:

@@ -27,6 +27,13 @@ class EncoderLayer(nn.Module):
             out = self.pos_ffn._forward_bf16(out)
         return out, attn, v
 
+    def _forward_cls_bf16(self, x):
+        """x bf16 [W,L,D] -> bf16 [W,D]: CLS row of this layer's output (valid only for the LAST layer)."""
+        out = self.slf_attn._forward_cls_bf16(x)
+        if self.FFN_need == True:  # noqa: E712
+            out = self.pos_ffn._forward_bf16(out.view(out.shape[0], 1, out.shape[1])).view(out.shape)
+        return out
+
     def forward(self, enc_input, slf_attn_mask=None, return_attn=False, return_attn_v=False):
         require_cuda(enc_input, "EncoderLayer")
         if slf_attn_mask is not None:

@@ -102,6 +102,19 @@ class MultiHeadAttention(nn.Module):
                 v = F.linear(x.float(), self.w_vs.weight).view(W, L, self.n_head, self.d_v).transpose(1, 2)
         return out, attn, v
 
+    def _forward_cls_bf16(self, x):
+        """Last-layer fast path: x bf16 [W,L,D] -> bf16 [W,D] (the CLS row of the block output)."""
+        if self.d_k != self.d_v:
+            raise NotImplementedError("lstc_vad_b200 attention requires d_k == d_v (all reference configs use 256)")
+        cfg = Fn.MHAConfig(n_head=self.n_head, d_k=self.d_k, layer_norm=self.layerNorm_flag == True,  # noqa: E712
+                           rel_mode=0,  # the CLS row / column of the rel-pos bias is zero
+                           attn_drop=Fn.next_dropout(self.attn_dropout.p, self.training),
+                           fc_drop=Fn.next_dropout(self.dropout.p, self.training))
+        has_table = self.relative_pe == True or self.relative_pe_2D == True  # noqa: E712
+        return Fn.MHAClsFn.apply(x, self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight,
+                                 self.layer_norm.weight, self.layer_norm.bias,
+                                 self.relative_position_bias_table if has_table else None, cfg)
+
     def forward(self, q, k, v, mask=None, return_attn=False, return_attn_v=False):
         require_cuda(q, "MultiHeadAttention")
         if mask is not None:

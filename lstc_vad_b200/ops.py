@@ -204,6 +204,58 @@ def attn_bwd(qkv: torch.Tensor, dout: torch.Tensor, W: int, L: int, H: int, dk: 
     return dqkv, dbias
 
 
+def attn_cls_fwd(q: torch.Tensor, kv: torch.Tensor, W: int, L: int, H: int, dk: int, scale: float,
+                 dropout: Dropout = NO_DROPOUT) -> torch.Tensor:
+    """CLS-query attention: q bf16 [W, H*dk], kv bf16 [W*L, 2*H*dk] (k | v column blocks) -> o bf16 [W, H*dk]."""
+    lib = _lib.load()
+    _cuda(q, "q", BF16)
+    _cuda(kv, "kv", BF16)
+    ldq, ldkv = _rowmajor2d(q, "q"), _rowmajor2d(kv, "kv")
+    HD = H * dk
+    if tuple(q.shape) != (W, HD) or tuple(kv.shape) != (W * L, 2 * HD):
+        raise RuntimeError(f"lstc_vad_b200.attn_cls_fwd: shapes {tuple(q.shape)}, {tuple(kv.shape)}")
+    out = torch.empty((W, HD), device=q.device, dtype=BF16)
+    p, seed, off = dropout
+    st = lib.lstc_attn_cls_fwd(_p(q), ldq, _p(kv), kv.data_ptr() + 2 * HD, ldkv, W, L, H, dk, float(scale), float(p),
+                               int(seed), int(off), _p(out), HD, _stream())
+    _lib.check(st, "lstc_attn_cls_fwd")
+    LAUNCHES.add(1)
+    return out
+
+
+def attn_cls_bwd(q: torch.Tensor, kv: torch.Tensor, dout: torch.Tensor, W: int, L: int, H: int, dk: int, scale: float,
+                 dropout: Dropout = NO_DROPOUT):
+    """-> (dq bf16 [W, H*dk], dkv bf16 [W*L, 2*H*dk])."""
+    lib = _lib.load()
+    _cuda(q, "q", BF16)
+    _cuda(kv, "kv", BF16)
+    _cuda(dout, "dout", BF16)
+    ldq, ldkv, ldo = _rowmajor2d(q, "q"), _rowmajor2d(kv, "kv"), _rowmajor2d(dout, "dout")
+    HD = H * dk
+    dq = torch.empty((W, HD), device=q.device, dtype=BF16)
+    dkv = torch.empty((W * L, 2 * HD), device=q.device, dtype=BF16)
+    p, seed, off = dropout
+    st = lib.lstc_attn_cls_bwd(_p(q), ldq, _p(kv), kv.data_ptr() + 2 * HD, ldkv, _p(dout), ldo, W, L, H, dk,
+                               float(scale), float(p), int(seed), int(off), _p(dq), HD, _p(dkv),
+                               dkv.data_ptr() + 2 * HD, 2 * HD, _stream())
+    _lib.check(st, "lstc_attn_cls_bwd")
+    LAUNCHES.add(1)
+    return dq, dkv
+
+
+def add_rows_(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst += src for 2-D bf16 row-strided views of equal shape."""
+    lib = _lib.load()
+    _cuda(dst, "dst", BF16)
+    _cuda(src, "src", BF16)
+    ldd, lds = _rowmajor2d(dst, "dst"), _rowmajor2d(src, "src")
+    if dst.shape != src.shape:
+        raise RuntimeError("lstc_vad_b200.add_rows_: shape mismatch")
+    st = lib.lstc_add_rows_bf16(_p(dst), ldd, _p(src), lds, dst.shape[0], dst.shape[1], _stream())
+    _lib.check(st, "lstc_add_rows_bf16")
+    LAUNCHES.add(1)
+
+
 # ------------------------------------------------------------------------------------------ LayerNorm
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, out_dtype=BF16):
     """x [..., D] bf16|fp32 -> (y, mean[rows], rstd[rows])."""

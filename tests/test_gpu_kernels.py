@@ -448,3 +448,40 @@ def test_threshold_labels_bit_exact(ops):
     s[:10] = 0.65
     out = ops.threshold_labels(s, 0.65)
     assert torch.equal(out, torch.where(s > 0.65, s, torch.zeros_like(s)))
+
+
+# ------------------------------------------------------------------------------------------ CLS-query attention
+@pytest.mark.parametrize("W,L,H,dk", [(3, 49, 8, 256), (5, 19, 8, 256), (2, 81, 8, 256), (4, 17, 2, 64), (1, 1, 1, 128),
+                                      (300, 49, 8, 256), (2, 96, 2, 256)])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_attn_cls_matches_row0_of_full_attention(ops, W, L, H, dk, p):
+    HD = H * dk
+    qkv = _rand((W * L, 3 * HD), 1.0, 70)
+    scale = 1.0 / math.sqrt(dk)
+    drop = (p, 777, 9) if p > 0 else ops.NO_DROPOUT
+    keep = ops.dropout_mask(W * H * L, L, drop).float() if p > 0 else None
+    qr = qkv.float().requires_grad_(True)
+    ref_o, _ = _attn_ref(qr, W, L, H, dk, None, scale, keep, p)
+    ref_cls = ref_o.view(W, L, HD)[:, 0, :]
+    dout = _rand((W, HD), 1.0, 71)
+    ref_cls.backward(dout.float())
+    q_cls = qkv.view(W, L, 3 * HD)[:, 0, :HD].contiguous()
+    kv = qkv[:, HD:].contiguous()
+    o = ops.attn_cls_fwd(q_cls, kv, W, L, H, dk, scale, drop)
+    assert_close(f"attn cls fwd W{W} L{L} H{H} dk{dk} p{p}", o, ref_cls, rtol=2e-2, atol=2e-2)
+    dq, dkv = ops.attn_cls_bwd(q_cls, kv, dout, W, L, H, dk, scale, drop)
+    g = qr.grad.view(W, L, 3 * HD)
+    gmax = max(g.abs().max().item(), 1e-3)
+    assert_close("attn cls bwd dq", dq, g[:, 0, :HD], rtol=3e-2, atol=3e-2 * gmax)
+    # rows 1.. of the q-gradient are zero in the reference (only the CLS query was used)
+    assert g[:, 1:, :HD].abs().max().item() == 0 if L > 1 else True
+    assert_close("attn cls bwd dkv", dkv.view(W, L, 2 * HD), g[:, :, HD:], rtol=3e-2, atol=3e-2 * gmax)
+
+
+def test_add_rows(ops):
+    a = _rand((40, 49 * 64), 1.0, 72)
+    b = _rand((40, 64), 1.0, 73)
+    ref = a.float().clone()
+    ref[:, :64] += b.float()
+    ops.add_rows_(a[:, :64], b)
+    assert_close("add rows", a, ref, rtol=1e-2, atol=1e-2)

@@ -106,7 +106,9 @@ def test_frame_level_auc_delta_against_oracle(setup):
     videos, frame_labels, esd, csd, cfg, enc, cls = setup
     ref = oracle_scores(esd, csd, cfg, videos, backshift=True)
     got = score_videos(enc, cls, videos, part_len=T, backshift=True)
+    fast = score_videos(enc, cls, videos, part_len=T, backshift=True, cls_fast_path=True)
     keys = sorted(videos)
+    assert max((fast[k] - got[k]).abs().max().item() for k in keys) <= 3e-3  # CLS fast path == full path
     for k in keys:
         assert got[k].shape == ref[k].shape == (videos[k].shape[0],)
     diff = max((got[k] - ref[k]).abs().max().item() for k in keys)
