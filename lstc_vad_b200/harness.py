@@ -234,8 +234,8 @@ class _InjectGrad(torch.autograd.Function):
 # Train/temporal_transformer_shanghaitech.py:76-78)
 # --------------------------------------------------------------------------------------------------
 class BucketedGradReducer:
-    """One bucket per EncoderLayer (+ one for everything else), reduced in reverse layer order as soon as the
-    last gradient of the bucket has been accumulated.  The bucket plan is static and only contains parameters
+    """Two buckets per EncoderLayer (FFN, attention) + one for everything else, reduced in reverse layer order as
+    soon as the last gradient of the bucket has been accumulated.  The bucket plan is static and only contains parameters
     that receive gradients (LayerNorms switched off by the model flags never do — SURVEY.md §8)."""
 
     def __init__(self, modules: Sequence[torch.nn.Module], process_group, comm_stream: Optional[torch.cuda.Stream] = None):
@@ -260,9 +260,21 @@ class BucketedGradReducer:
             in_layers = set()
             if stack is not None:
                 for layer in stack:
-                    ps = [p for p in layer.parameters() if p.requires_grad]
-                    in_layers.update(id(p) for p in ps)
-                    self.buckets.append(ps)
+                    # two buckets per layer: the FFN gradients are complete before the attention block's backward
+                    # starts, so their all-reduce overlaps it; the last exposed bucket is half a layer, not a layer
+                    subs = [getattr(layer, "pos_ffn", None), getattr(layer, "slf_attn", None)]
+                    seen = set()
+                    for sub in subs:
+                        if sub is None:
+                            continue
+                        ps = [p for p in sub.parameters() if p.requires_grad]
+                        seen.update(id(p) for p in ps)
+                        if ps:
+                            self.buckets.append(ps)
+                    rest_l = [p for p in layer.parameters() if p.requires_grad and id(p) not in seen]
+                    if rest_l:
+                        self.buckets.append(rest_l)
+                    in_layers.update(id(p) for p in layer.parameters())
             rest += [p for p in m.parameters() if p.requires_grad and id(p) not in in_layers]
         if rest:
             self.buckets.append(rest)
