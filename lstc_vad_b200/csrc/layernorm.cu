@@ -58,7 +58,43 @@ __device__ __forceinline__ void block_sum_n(float (&v)[N], float (*buf)[MAX_WARP
   phase ^= 1;
 }
 
-constexpr int RPI = 2;  // rows per CTA iteration: twice the bytes in flight, half the barriers per row
+constexpr int RPI = 2;   // forward: rows per CTA iteration (half the barriers per row)
+constexpr int NSTG = 4;  // depth of the per-thread cp.async row ring
+
+// Every thread stages ITS OWN 16/32-byte chunks of the next NSTG-1 iterations in shared memory with cp.async and is
+// the only reader of those bytes, so the ring needs no barrier: cp.async.wait_group on the thread's own groups is
+// enough.  This keeps ~3 rows per CTA in flight without holding them in registers.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <bool IS_F32>
+__device__ __forceinline__ void stage8(uint32_t dst, const void* base, int64_t off) {
+  if (IS_F32) {
+    cp_async16(dst, reinterpret_cast<const float*>(base) + off);
+    cp_async16(dst + 16, reinterpret_cast<const float*>(base) + off + 4);
+  } else {
+    cp_async16(dst, reinterpret_cast<const __nv_bfloat16*>(base) + off);
+  }
+}
+template <bool IS_F32>
+__device__ __forceinline__ void unstage8(uint32_t src, float (&f)[8]) {
+  uint4 a;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(src));
+  if (IS_F32) {
+    uint4 b;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(src + 16));
+    f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+    f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+  } else {
+    unpack8(a, f);
+  }
+}
 
 template <int NV, bool X_F32, bool Y_F32>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
@@ -66,8 +102,28 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int64_t rows, int D, float eps) {
   __shared__ float buf[2][MAX_WARPS][RPI];
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  constexpr int XB = X_F32 ? 32 : 16;
   int phase = 0;
   const int tid = threadIdx.x;
+  const uint32_t ring = smem_addr(ring_raw);
+  const uint32_t stage_bytes = RPI * NV * blockDim.x * XB;
+  auto slot = [&](int st, int r, int v) { return ring + st * stage_bytes + ((r * NV + v) * blockDim.x + tid) * XB; };
+  auto issue = [&](int64_t row0, int st) {
+    if (row0 < rows) {
+#pragma unroll
+      for (int r = 0; r < RPI; ++r) {
+        if (row0 + r < rows) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c = (v * blockDim.x + tid) * 8;
+            if (c < D) stage8<X_F32>(slot(st, r, v), x, (row0 + r) * D + c);
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
   float gm[NV][8], bt[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -78,7 +134,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
     }
   }
   const float invD = 1.0f / (float)D;
-  for (int64_t row0 = (int64_t)blockIdx.x * RPI; row0 < rows; row0 += (int64_t)gridDim.x * RPI) {
+  const int64_t step = (int64_t)gridDim.x * RPI;
+#pragma unroll
+  for (int i = 0; i < NSTG - 1; ++i) issue((int64_t)blockIdx.x * RPI + i * step, i);
+  int st = 0;
+  for (int64_t row0 = (int64_t)blockIdx.x * RPI; row0 < rows; row0 += step) {
+    cp_async_wait<NSTG - 2>();
     float xv[RPI][NV][8];
     float s[RPI];
 #pragma unroll
@@ -88,23 +149,16 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int c = (v * blockDim.x + tid) * 8;
-          if (c < D) load8<X_F32>(x, (row0 + r) * D + c, xv[r][v]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RPI; ++r) {
-      if (row0 + r < rows) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = (v * blockDim.x + tid) * 8;
           if (c < D) {
+            unstage8<X_F32>(slot(st, r, v), xv[r][v]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[r] += xv[r][v][j];
           }
         }
       }
     }
+    issue(row0 + (NSTG - 1) * step, st == 0 ? NSTG - 1 : st - 1);  // refills the slot consumed one iteration ago
+    st = (st + 1 == NSTG) ? 0 : st + 1;
     block_sum_n<RPI>(s, buf, phase);
     float mean[RPI], q[RPI];
 #pragma unroll
@@ -147,31 +201,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
       }
     }
   }
-}
-
-// raw (still packed) 8-element vector: prefetched one row ahead without paying for unpacked fp32 registers
-template <bool IS_F32>
-struct Raw8 {
-  uint4 a, b;  // bf16: only `a` is used
-};
-template <bool IS_F32>
-__device__ __forceinline__ void load_raw(const void* base, int64_t off, Raw8<IS_F32>& r) {
-  if (IS_F32) {
-    r.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + off));
-    r.b = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + off + 4));
-  } else {
-    r.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
-  }
-}
-template <bool IS_F32>
-__device__ __forceinline__ void unpack_raw(const Raw8<IS_F32>& r, float (&f)[8]) {
-  if (IS_F32) {
-    f[0] = __uint_as_float(r.a.x); f[1] = __uint_as_float(r.a.y); f[2] = __uint_as_float(r.a.z);
-    f[3] = __uint_as_float(r.a.w); f[4] = __uint_as_float(r.b.x); f[5] = __uint_as_float(r.b.y);
-    f[6] = __uint_as_float(r.b.z); f[7] = __uint_as_float(r.b.w);
-  } else {
-    unpack8(r.a, f);
-  }
+  cp_async_wait<0>();
 }
 
 template <int NV, bool DY_F32, bool X_F32, bool DX_F32>
@@ -181,8 +211,27 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
               __nv_bfloat16* __restrict__ dx_drop, float drop_scale, uint32_t drop_thr16, uint64_t seed,
               uint64_t offset, float* __restrict__ partial /*[grid][3][D]*/, int want_dxsum, int64_t rows, int D) {
   __shared__ float buf[2][MAX_WARPS][2];
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  constexpr int XB = X_F32 ? 32 : 16, YB = DY_F32 ? 32 : 16;
   int phase = 0;
   const int tid = threadIdx.x;
+  const uint32_t ring = smem_addr(ring_raw);
+  const uint32_t stage_bytes = NV * blockDim.x * (XB + YB);
+  auto x_slot = [&](int st, int v) { return ring + st * stage_bytes + (v * blockDim.x + tid) * XB; };
+  auto dy_slot = [&](int st, int v) { return ring + st * stage_bytes + NV * blockDim.x * XB + (v * blockDim.x + tid) * YB; };
+  auto issue = [&](int64_t row, int st) {
+    if (row < rows) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = (v * blockDim.x + tid) * 8;
+        if (c < D) {
+          stage8<X_F32>(x_slot(st, v), x, row * D + c);
+          stage8<DY_F32>(dy_slot(st, v), dy, row * D + c);
+        }
+      }
+    }
+    cp_async_commit();
+  };
   float gm[NV][8], dg[NV][8], db[NV][8], dxs[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -197,44 +246,31 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
   }
   const float invD = 1.0f / (float)D;
   const int64_t ld8 = D >> 3;
-  // software pipeline: the (packed) operands of the next row are in flight while this row is reduced
-  Raw8<X_F32> nx[NV];
-  Raw8<DY_F32> ndy[NV];
-  float nmean = 0.f, nrstd = 0.f;
-  int64_t row = blockIdx.x;
-  if (row < rows) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-        load_raw<X_F32>(x, row * D + c, nx[v]);
-        load_raw<DY_F32>(dy, row * D + c, ndy[v]);
-      }
-    }
+  for (int i = 0; i < NSTG - 1; ++i) issue((int64_t)blockIdx.x + (int64_t)i * gridDim.x, i);
+  int st = 0;
+  int64_t row = blockIdx.x;
+  float nmean = 0.f, nrstd = 0.f;
+  if (row < rows) {
     nmean = __ldg(mean_in + row);
     nrstd = __ldg(rstd_in + row);
   }
   for (; row < rows; row += gridDim.x) {
+    cp_async_wait<NSTG - 2>();
     float xh[NV][8], dyg[NV][8];
     const float mean = nmean, rstd = nrstd;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = (v * blockDim.x + tid) * 8;
       if (c < D) {
-        unpack_raw<X_F32>(nx[v], xh[v]);
-        unpack_raw<DY_F32>(ndy[v], dyg[v]);
+        unstage8<X_F32>(x_slot(st, v), xh[v]);
+        unstage8<DY_F32>(dy_slot(st, v), dyg[v]);
       }
     }
+    issue(row + (int64_t)(NSTG - 1) * gridDim.x, st == 0 ? NSTG - 1 : st - 1);  // slot consumed one iteration ago
+    st = (st + 1 == NSTG) ? 0 : st + 1;
     const int64_t nrow = row + gridDim.x;
     if (nrow < rows) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = (v * blockDim.x + tid) * 8;
-        if (c < D) {
-          load_raw<X_F32>(x, nrow * D + c, nx[v]);
-          load_raw<DY_F32>(dy, nrow * D + c, ndy[v]);
-        }
-      }
       nmean = __ldg(mean_in + nrow);
       nrstd = __ldg(rstd_in + nrow);
     }
@@ -283,6 +319,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
       }
     }
   }
+  cp_async_wait<0>();
   float* pg = partial + (int64_t)blockIdx.x * 3 * D;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -338,9 +375,10 @@ static int64_t bwd_grid_max(int64_t rows) {
   return g;
 }
 template <typename K>
-static int64_t resident_grid(K kern, int threads, int64_t work, int cap_per_sm) {
+static int64_t resident_grid(K kern, int threads, size_t smem, int64_t work, int cap_per_sm) {
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
   if (occ > cap_per_sm) occ = cap_per_sm;
   int64_t g = (int64_t)num_sms() * occ;
   if (g > work) g = work;
@@ -367,8 +405,9 @@ extern "C" int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamm
 #define LSTC_LN_FWD_K(NV, A, B)                                                                       \
   do {                                                                                                \
     auto kern = ln::ln_fwd_kernel<NV, A, B>;                                                          \
-    const int64_t grid = ln::resident_grid(kern, threads, iters, 8);                                  \
-    kern<<<(unsigned)grid, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, (int)D, eps);   \
+    const size_t smem = (size_t)ln::NSTG * ln::RPI * NV * threads * (A ? 32 : 16);                    \
+    const int64_t grid = ln::resident_grid(kern, threads, smem, iters, 8);                            \
+    kern<<<(unsigned)grid, threads, smem, stream>>>(x, gamma, beta, y, mean, rstd, rows, (int)D, eps); \
   } while (0)
 #define LSTC_LN_FWD(NV)                                         \
   do {                                                          \
@@ -416,8 +455,9 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
 #define LSTC_LN_BWD_K(NV, A, B, C)                                                                             \
   do {                                                                                                         \
     auto kern = ln::ln_bwd_kernel<NV, A, B, C>;                                                                \
-    grid = ln::resident_grid(kern, threads, rows, 8);                                                          \
-    kern<<<(unsigned)grid, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dx, dd, dscale, thr, seed, offset,  \
+    const size_t smem = (size_t)ln::NSTG * NV * threads * ((B ? 32 : 16) + (A ? 32 : 16));                     \
+    grid = ln::resident_grid(kern, threads, smem, rows, 8);                                                    \
+    kern<<<(unsigned)grid, threads, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dd, dscale, thr, seed, offset, \
                                                  partial, dxsum != nullptr ? 1 : 0, rows, (int)D);             \
   } while (0)
 #define LSTC_LN_BWD(NV)                                             \

@@ -15,6 +15,7 @@ parameter version), GEMMs accumulate in fp32, LayerNorm / softmax / losses compu
 from __future__ import annotations
 
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -78,12 +79,16 @@ class WeightCache:
         if cacheable:
             with self._lock:
                 hit = self._d.get(key)
-            if hit is not None and hit[0] == sig:
+            # identity is checked through weak references: `id()` and the storage address of a dead parameter can
+            # both be recycled by a new one with the same shape and version
+            if hit is not None and hit[0] == sig and all(r() is p for r, p in zip(hit[2], params)):
                 return hit[1]
         val = build()
         if cacheable:
             with self._lock:
-                self._d[key] = (sig, val)
+                if len(self._d) > 4096:  # entries of dead modules
+                    self._d = {k: v for k, v in self._d.items() if all(r() is not None for r in v[2])}
+                self._d[key] = (sig, val, tuple(weakref.ref(p) for p in params))
         return val
 
     def bf16(self, p: torch.Tensor, pad_rows: int = 0, pad_cols: int = 0) -> torch.Tensor:
@@ -128,13 +133,28 @@ def invalidate_weight_cache() -> None:
     CACHE.invalidate()
 
 
-def _wgrad_split(n_out: int, k_out: int, m_red: int) -> int:
-    """split-K factor for a weight gradient [n_out, k_out] reduced over m_red rows: aim at ~4 work items per
-    SM while keeping >= 4 k-blocks (of 64 rows) per split."""
-    bn = 256 if k_out > 128 else (128 if k_out > 64 else 64)
-    tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
+def _wgrad_split(n_out: int, k_out: int, m_red: int, n_units: int = 74) -> int:
+    """split-K factor for a weight gradient [n_out, k_out] reduced over m_red rows.  The persistent GEMM runs on
+    `n_units` CTA pairs (74 on a B200); work items = output tiles x splits are executed in waves of n_units, so the
+    smallest split whose last wave is >= 95 % full is chosen (e.g. 64 tiles -> 8 splits = 512 items = 6.92 waves),
+    keeping >= 4 k-blocks of 64 rows per split."""
+    if k_out > 128 and n_out > 128:
+        tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)    # CTA-pair kernel: 256 x 256 tiles
+    else:
+        bn = 256 if k_out > 128 else (128 if k_out > 64 else 64)
+        tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
+        n_units = 148
     num_kb = (m_red + 63) // 64
-    return max(1, min(592 // max(tiles, 1), num_kb // 4, 32))
+    max_split = max(1, min(32, num_kb // 4))
+    best, best_eff = 1, 0.0
+    for s in range(1, max_split + 1):
+        items = tiles * s
+        eff = items / (((items + n_units - 1) // n_units) * n_units)
+        if eff >= 0.95:
+            return s
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return best
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:

@@ -114,3 +114,26 @@ def test_dropout_stream_is_deterministic_and_distinct():
     b = [Fn.next_dropout(0.2, True) for _ in range(3)]
     assert a == b and len({x[2] for x in a}) == 3
     assert Fn.next_dropout(0.2, False) == Fn.NO_DROPOUT and Fn.next_dropout(0.0, True) == Fn.NO_DROPOUT
+
+
+def test_weight_cache_is_not_fooled_by_recycled_parameters():
+    """A new Parameter can reuse the id() / storage address / version of a dead one; the cache must miss."""
+    from lstc_vad_b200.functional import WeightCache
+    cache = WeightCache()
+    built = []
+
+    def get(p):
+        return cache._get(("bf16", id(p), None, 0, 0), (p,), lambda: built.append(1) or float(p.sum()))
+
+    p = torch.nn.Parameter(torch.ones(4, 4))
+    assert get(p) == 16.0 and get(p) == 16.0 and len(built) == 1      # second call is a hit
+    key_id, ptr = id(p), p.data_ptr()
+    del p
+    for _ in range(64):  # try to get an object with the same id / storage
+        q = torch.nn.Parameter(torch.full((4, 4), 2.0))
+        if id(q) == key_id or q.data_ptr() == ptr:
+            break
+    assert get(q) == 32.0                                             # never the stale 16.0
+    with torch.no_grad():
+        q.add_(1.0)                                                   # optimizer-style in-place update bumps _version
+    assert get(q) == 48.0
