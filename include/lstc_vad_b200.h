@@ -196,6 +196,12 @@ int lstc_dropout_mask(uint8_t* mask, int64_t rows, int64_t cols, float p, uint64
                       void* stream);
 /* dst[i] = src[i] * (*scalar_dev) */
 int lstc_scale_by_device_scalar(const float* src, const float* scalar_dev, float* dst, int64_t n, void* stream);
+/* Temporal pooling of a video into n_bins pseudo-clips + optional L2 normalisation of every token
+ * (Test/evaluation_UCF.py:52-77: r = linspace(0, n_clips, 33); bin b = mean(feats[r[b]:r[b+1]]), or the single clip
+ * feats[r[b]] when the bin is empty; F.normalize(p=2, dim=-1)).
+ *   feats fp32 [n_clips, n_patch, D] ; bounds int32 [n_bins+1] (device) ; out fp32 [n_bins, n_patch, D] */
+int lstc_segment_mean(const float* feats, const int32_t* bounds, int n_bins, int64_t n_clips, int n_patch, int D,
+                      int l2norm, float* out, void* stream);
 /* Fused multi-tensor-free Adagrad step on one flat fp32 tensor (torch.optim.Adagrad semantics,
  * Train/temporal_transformer_shanghaitech.py:83-85,142): g += wd * p ; state += g*g ;
  * p -= lr * g / (sqrt(state) + eps).

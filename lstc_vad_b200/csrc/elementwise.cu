@@ -306,10 +306,51 @@ __global__ void adagrad_kernel(float* __restrict__ p, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------- UCF-style temporal pooling
+// out[b, p, :] = l2norm?( mean_{c in [lo_b, hi_b)} feats[c, p, :] )  with the single clip lo_b when the bin is empty
+// (Test/evaluation_UCF.py:54,66-71,77).  grid (bins, patches); thread owns columns tid, tid+blockDim, ...
+__global__ void segment_mean_kernel(const float* __restrict__ feats, const int32_t* __restrict__ bounds, int64_t n_clips,
+                                    int n_patch, int D, int l2norm, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, pch = blockIdx.y;
+  int lo = bounds[b], hi = bounds[b + 1];
+  if (hi <= lo) hi = lo + 1;
+  if (lo >= n_clips) lo = (int)n_clips - 1;
+  if (hi > n_clips) hi = (int)n_clips;
+  const float inv = 1.0f / (float)(hi - lo);
+  float ss = 0.f;
+  float* orow = out + ((int64_t)b * n_patch + pch) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int c = lo; c < hi; ++c) acc += feats[((int64_t)c * n_patch + pch) * D + d];
+    acc *= inv;
+    orow[d] = acc;
+    ss += acc * acc;
+  }
+  if (!l2norm) return;
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float scale = 1.0f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize(p=2, dim=-1): x / max(||x||, eps)
+  for (int d = threadIdx.x; d < D; d += blockDim.x) orow[d] *= scale;
+}
+
 }  // namespace ew
 }  // namespace lstc
 
 using namespace lstc;
+
+extern "C" int lstc_segment_mean(const float* feats, const int32_t* bounds, int n_bins, int64_t n_clips, int n_patch,
+                                 int D, int l2norm, float* out, void* stream) {
+  LSTC_CHECK_ARG(feats && bounds && out, "lstc_segment_mean: null pointer");
+  LSTC_CHECK_ARG(n_bins >= 1 && n_clips >= 1 && n_patch >= 1 && D >= 1, "lstc_segment_mean: empty input");
+  ew::segment_mean_kernel<<<dim3((unsigned)n_bins, (unsigned)n_patch), 256, 0, (cudaStream_t)stream>>>(
+      feats, bounds, n_clips, n_patch, D, l2norm, out);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
 
 extern "C" int lstc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   LSTC_CHECK_ARG(n == 0 || (src && dst), "lstc_cast_f32_to_bf16: null pointer");

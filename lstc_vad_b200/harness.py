@@ -438,3 +438,15 @@ def frame_scores(clip_scores: torch.Tensor, segment_len: int = 16) -> torch.Tens
     """Per-clip scores -> per-frame scores (each clip covers `segment_len` frames), as the evaluation loop does
     (Test/evaluation_shanghaitech_ubnormal.py:92)."""
     return clip_scores.repeat_interleave(segment_len)
+
+
+def pool_video_bins(feats: torch.Tensor, n_bins: int = 32, l2norm: bool = True) -> Tuple[torch.Tensor, List[int]]:
+    """UCF-Crime evaluation pooling (Test/evaluation_UCF.py:52-77): a video of n_clips clips becomes `n_bins` pseudo
+    clips, bin b = mean of clips [r[b], r[b+1]) with r = linspace(0, n_clips, n_bins+1) truncated to int32 (the single
+    clip r[b] when the bin is empty), every token L2-normalised.  Returns (pooled fp32 [n_bins, n_patch, D] on the
+    GPU, r as a list — the evaluation loop needs it to expand bin scores back to frames)."""
+    import numpy as np
+    n_clips = feats.shape[0]
+    r = np.linspace(0, n_clips, n_bins + 1, dtype=np.int32)
+    bounds = torch.from_numpy(r).to(feats.device)
+    return ops.segment_mean(feats.float(), bounds, l2norm), r.tolist()

@@ -544,6 +544,22 @@ def scale_by_device_scalar(src: torch.Tensor, scalar: torch.Tensor) -> torch.Ten
     return dst
 
 
+def segment_mean(feats: torch.Tensor, bounds: torch.Tensor, l2norm: bool = False) -> torch.Tensor:
+    """feats fp32 [n_clips, n_patch, D], bounds int32 [n_bins+1] -> fp32 [n_bins, n_patch, D] (bin means, empty bin =
+    its first clip; optional per-token L2 normalisation)."""
+    lib = _lib.load()
+    _cuda(feats, "feats", F32)
+    _cuda(bounds, "bounds", torch.int32)
+    feats, bounds = feats.contiguous(), bounds.contiguous()
+    n_clips, n_patch, D = feats.shape
+    n_bins = bounds.numel() - 1
+    out = torch.empty((n_bins, n_patch, D), device=feats.device, dtype=F32)
+    st = lib.lstc_segment_mean(_p(feats), _p(bounds), n_bins, n_clips, n_patch, D, int(l2norm), _p(out), _stream())
+    _lib.check(st, "lstc_segment_mean")
+    LAUNCHES.add(1)
+    return out
+
+
 def grad_clip_coef(grads, max_norm: float) -> torch.Tensor:
     """Device scalar min(1, max_norm / (||grads||_2 + 1e-6)) over a list of fp32 tensors — clip_grad_norm_ without a
     host sync (the coefficient is consumed by adagrad_step)."""

@@ -295,3 +295,21 @@ def window_bounds(n_clips: int, part_len: int, backshift: bool) -> List[Tuple[in
         else:
             out.append((beg, end))
     return out
+
+
+def pool_video_bins(feats: Tensor, n_bins: int = 32, l2norm: bool = True):
+    """Test/evaluation_UCF.py:52-77: r = np.linspace(0, n_clips, n_bins + 1, dtype=int32); bin b is the mean of clips
+    [r[b], r[b+1]) — or the single clip r[b] when the bin is empty — then F.normalize(p=2, dim=-1) per token.
+    feats [n_clips, n_patch, D] -> ([n_bins, n_patch, D], r)."""
+    n_clips = feats.shape[0]
+    r = np.linspace(0, n_clips, n_bins + 1, dtype=np.int32)
+    rows = []
+    for b in range(n_bins):
+        if r[b] == r[b + 1]:
+            rows.append(feats[r[b]])
+        else:
+            rows.append(feats[r[b]:r[b + 1]].mean(dim=0))
+    out = torch.stack(rows)
+    if l2norm:
+        out = F.normalize(out, p=2, dim=-1)
+    return out, r.tolist()

@@ -185,3 +185,16 @@ def test_train_steps_with_fused_adagrad_track_torch_adagrad():
     for (na, pa), (nb, pb) in zip(a.encoder.named_parameters(), b.encoder.named_parameters()):
         assert na == nb
         assert torch.allclose(pa, pb, rtol=1e-3, atol=2e-5), na
+
+
+@pytest.mark.parametrize("n_clips", [7, 32, 33, 100, 517])
+def test_ucf_bin_pooling_matches_oracle(n_clips):
+    from lstc_vad_b200.harness import pool_video_bins
+    feats = torch.randn(n_clips, 9, 256, generator=torch.Generator().manual_seed(n_clips)).abs()
+    ref, r_ref = O.pool_video_bins(feats, 32, True)
+    got, r = pool_video_bins(feats.cuda(), 32, True)
+    assert r == r_ref
+    assert (got.cpu() - ref).abs().max().item() < 1e-6
+    ref2, _ = O.pool_video_bins(feats, 32, False)
+    got2, _ = pool_video_bins(feats.cuda(), 32, False)
+    assert (got2.cpu() - ref2).abs().max().item() < 1e-5
