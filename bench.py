@@ -24,7 +24,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "windows/sec fwd+bwd (LTN, d_model 2048)"
+METRIC = "windows/sec fwd+bwd (LTN, d_model 2048)"  # the headline workload; --workload runs the other configs
 UNIT = "windows/s"
 
 
@@ -222,11 +222,11 @@ def main():
     B = args.batch_size or wl.batch_size
 
     step = TrainStep(wl, dev, seed=0, train_mode=not args.eval_mode, process_group=pg)
-    W = 2 * B * wl.part_num
+    W = 2 * B * wl.part_num * (1 if wl.kind == "ltn" else wl.part_len)
     # two distinct host batches (pinned) — rank-dependent seeds; resident device copies for the kernel-side number
     host = [synthetic_step_inputs(wl, seed=100 + 10 * rank + i, batch_size=B, pin=True) for i in range(2)]
-    resident = [(f.to(dev), l.to(dev)) for f, l in host]
-    in_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    resident = [(f.to(dev), l.to(dev) if l is not None else None) for f, l in host]
+    in_bytes = host[0][0].numel() * 4 + (host[0][1].numel() * 4 if host[0][1] is not None else 0)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -275,7 +275,8 @@ def main():
 
     # ---------------- end-to-end: pinned host inputs, H2D each step (double-buffered), D2H of the loss -------------
     copy_stream = torch.cuda.Stream()
-    dbuf = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
+    dbuf = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1]) if resident[0][1] is not None else None)
+            for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -284,7 +285,8 @@ def main():
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[s])
             dbuf[s][0].copy_(host[s][0], non_blocking=True)
-            dbuf[s][1].copy_(host[s][1], non_blocking=True)
+            if host[s][1] is not None:
+                dbuf[s][1].copy_(host[s][1], non_blocking=True)
             ready[s].record(copy_stream)
 
     for s in range(2):
@@ -391,9 +393,9 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops_sustained"]) if achieved else None,
                          # mean dram__bytes_read+write per GEMM launch over the 40 launches of one step (ncu capture in
-                         # profiles/r1_step_launches_traffic_v4.txt; algorithmic operand+result bytes average 0.80 GB)
-                         "traffic": 0.949e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
-                         "kernel": "gemm_bf16_tcgen05_kernel (all launches of the timed region)",
+                         # profiles/r1_step_launches_traffic_v5_2cta.txt; algorithmic operand+result bytes average 0.80 GB)
+                         "traffic": 1.041e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
+                         "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM launches of the pass)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained", "gemm_share_of_step": gms / ms_prof,
                          "measured": "CUDA-event pair around every GEMM launch during a second timed pass of the same K "
                                      "steps (ms_per_step of that pass: %.2f); the headline pass runs without per-launch "
