@@ -1,5 +1,5 @@
 import torch, math, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from lstc_vad_b200 import ops
 from tests._util import report
 torch.manual_seed(0)

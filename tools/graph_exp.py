@@ -1,6 +1,6 @@
 """Experiment: how much does CUDA-graph replay of the whole fwd+bwd step gain over eager launches? (dropout off)"""
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from lstc_vad_b200.harness import TrainStep, WORKLOADS, synthetic_step_inputs
 from lstc_vad_b200 import functional as Fn
 wl = WORKLOADS['ltn_sht']
