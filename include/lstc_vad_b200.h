@@ -177,6 +177,13 @@ int lstc_soft_ce_loss(const float* probs, const float* labels, int64_t n, int C,
 int lstc_bce_loss(const float* scores, const float* labels, int64_t n_parts, int T, float w_normal,
                   float w_abnormal, float* out1, float* dscores, void* stream);
 int lstc_threshold_labels(const float* scores, float thr, float* out, int64_t n, void* stream);
+/* Frame-level ROC-AUC (utils/eval_utils.py:21-24: sklearn roc_curve + auc over per-frame scores) computed from
+ * per-WINDOW scores: every frame of a window carries the window's score
+ * (Test/evaluation_shanghaitech_ubnormal.py:92-94), so window i contributes pos_w[i] positive and neg_w[i] negative
+ * frames at threshold scores[i]; equal scores form one ROC step, exactly like sklearn's distinct-threshold curve.
+ * out3 (device, fp64) = {auc, total positive frames, total negative frames}.  n <= 16384 windows. */
+int lstc_weighted_auc(const float* scores, const float* pos_w, const float* neg_w, int64_t n, double* out3,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small utilities used between the kernels above.

@@ -42,6 +42,7 @@ SIGNATURES: dict[str, tuple] = {
     "lstc_soft_ce_loss": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "lstc_bce_loss": (_I, [_P, _P, _L, _I, _F, _F, _P, _P, _P]),
     "lstc_threshold_labels": (_I, [_P, _F, _P, _L, _P]),
+    "lstc_weighted_auc": (_I, [_P, _P, _P, _L, _P, _P]),
     "lstc_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
     "lstc_cast_bf16_to_f32": (_I, [_P, _P, _L, _P]),
     "lstc_colsum_workspace": (_L, [_L, _L]),

@@ -35,8 +35,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
     float f[8];
     unpack8(v, f);
-    reinterpret_cast<float4*>(dst)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
-    reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    __stcs(reinterpret_cast<float4*>(dst) + 2 * i, make_float4(f[0], f[1], f[2], f[3]));
+    __stcs(reinterpret_cast<float4*>(dst) + 2 * i + 1, make_float4(f[4], f[5], f[6], f[7]));
   }
   for (int64_t i = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = __bfloat162float(src[i]);
@@ -150,7 +150,24 @@ __global__ void colsum_stage1_kernel(const __nv_bfloat16* __restrict__ x, int64_
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < cols) {
     const bool vec = (c + 8 <= cols) && (ld % 8 == 0);
-    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
+    const int64_t rstep = (int64_t)gridDim.y * 8;
+    int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y;
+    if (vec) {
+      // 4 independent 16-byte loads in flight per thread
+      for (; r + 3 * rstep < rows; r += 4 * rstep) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * rstep) * ld + c));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+      }
+    }
+    for (; r < rows; r += rstep) {
       if (vec) {
         float f[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * ld + c)), f);

@@ -26,14 +26,16 @@ __device__ __forceinline__ void load8(const void* base, int64_t off, float (&f)[
     unpack8(v, f);
   }
 }
+// streaming (evict-first) stores: the row is not re-read by this kernel and is larger than what L2 can keep for the
+// consumer anyway; keeping it from displacing the rows still to be read helps the read stream
 template <bool IS_F32>
 __device__ __forceinline__ void store8(void* base, int64_t off, const float (&f)[8]) {
   if (IS_F32) {
     float* p = reinterpret_cast<float*>(base) + off;
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    __stcs(reinterpret_cast<float4*>(p), make_float4(f[0], f[1], f[2], f[3]));
+    __stcs(reinterpret_cast<float4*>(p + 4), make_float4(f[4], f[5], f[6], f[7]));
   } else {
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = pack8(f);
+    __stcs(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off), pack8(f));
   }
 }
 

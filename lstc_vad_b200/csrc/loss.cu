@@ -169,10 +169,79 @@ bce_kernel(const float* __restrict__ scores, const float* __restrict__ lab, int6
   if (threadIdx.x == 0) out1[0] = total * invn;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Frame-level ROC-AUC from per-window scores (utils/eval_utils.py:21-24 = sklearn roc_curve + auc on per-frame
+// scores; every frame of a window carries the window's score, Test/evaluation_shanghaitech_ubnormal.py:92-94, so the
+// frame-level curve only has one threshold per distinct WINDOW score: sort the windows by score (descending), walk
+// the groups of equal scores accumulating positive / negative frame counts and add one trapezoid per group).
+// One CTA: bitonic sort of (score, index) in shared memory, then a sequential fp64 trapezoid walk.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+weighted_auc_kernel(const float* __restrict__ scores, const float* __restrict__ pos_w, const float* __restrict__ neg_w,
+                    int n, int npad, double* __restrict__ out /* auc, total_pos, total_neg */) {
+  extern __shared__ float sm[];
+  float* key = sm;                                   // [npad]
+  int* idx = reinterpret_cast<int*>(sm + npad);      // [npad]
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    key[i] = i < n ? scores[i] : -INFINITY;
+    idx[i] = i < n ? i : -1;
+  }
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool desc = (i & k) == 0;  // overall order: descending
+          const float a = key[i], b = key[l];
+          // ties broken by index so the sort is deterministic (the AUC itself does not depend on the tie order)
+          const bool a_first = (a > b) || (a == b && idx[i] < idx[l]);
+          if (desc ? !a_first : a_first) {
+            key[i] = b; key[l] = a;
+            const int t = idx[i]; idx[i] = idx[l]; idx[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    double tp = 0, fp = 0, tp_prev = 0, fp_prev = 0, area = 0;
+    int i = 0;
+    while (i < n) {
+      const float s = key[i];
+      while (i < n && key[i] == s) {
+        tp += (double)pos_w[idx[i]];
+        fp += (double)neg_w[idx[i]];
+        ++i;
+      }
+      area += (fp - fp_prev) * (tp + tp_prev) * 0.5;
+      tp_prev = tp;
+      fp_prev = fp;
+    }
+    out[0] = (tp > 0 && fp > 0) ? area / (tp * fp) : nan("");
+    out[1] = tp;
+    out[2] = fp;
+  }
+}
+
 }  // namespace loss
 }  // namespace lstc
 
 using namespace lstc;
+
+extern "C" int lstc_weighted_auc(const float* scores, const float* pos_w, const float* neg_w, int64_t n, double* out3,
+                                 void* stream) {
+  LSTC_CHECK_ARG(scores && pos_w && neg_w && out3, "lstc_weighted_auc: null pointer");
+  LSTC_CHECK_ARG(n >= 1 && n <= 16384, "lstc_weighted_auc: n=%lld windows outside [1, 16384] (single-CTA sort)", (long long)n);
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  const size_t smem = (size_t)npad * 8;
+  LSTC_CHECK_CUDA(cudaFuncSetAttribute(loss::weighted_auc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  loss::weighted_auc_kernel<<<1, loss::THREADS, smem, (cudaStream_t)stream>>>(scores, pos_w, neg_w, (int)n, npad, out3);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
 
 extern "C" int lstc_mil_loss(const float* scores, int64_t stride, int B, int P, int T, int topk, float lambda1,
                              int64_t spar_start, float* out3, int32_t* top_idx, float* dscores, void* stream) {

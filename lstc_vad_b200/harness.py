@@ -450,3 +450,13 @@ def pool_video_bins(feats: torch.Tensor, n_bins: int = 32, l2norm: bool = True) 
     r = np.linspace(0, n_clips, n_bins + 1, dtype=np.int32)
     bounds = torch.from_numpy(r).to(feats.device)
     return ops.segment_mean(feats.float(), bounds, l2norm), r.tolist()
+
+
+def frame_level_auc(window_scores: torch.Tensor, pos_frames: torch.Tensor, neg_frames: torch.Tensor) -> float:
+    """Frame-level ROC-AUC of a scored corpus without materialising per-frame arrays or leaving the GPU for the sort:
+    window i has score window_scores[i] and covers pos_frames[i] anomalous + neg_frames[i] normal frames (the reference
+    repeats each window score over its frames and calls sklearn, Test/evaluation_shanghaitech_ubnormal.py:92-96,
+    utils/eval_utils.py:21-24).  Up to 16384 windows per call."""
+    dev = window_scores.device
+    out = ops.weighted_auc(window_scores.float(), pos_frames.to(dev).float(), neg_frames.to(dev).float())
+    return float(out[0].item())

@@ -457,6 +457,22 @@ def bce_loss(scores: torch.Tensor, labels: torch.Tensor, T: int, w_normal: float
     return out1, dscores
 
 
+def weighted_auc(scores: torch.Tensor, pos_w: torch.Tensor, neg_w: torch.Tensor) -> torch.Tensor:
+    """ROC-AUC of n scored groups, group i holding pos_w[i] positives and neg_w[i] negatives that all carry
+    scores[i].  -> fp64 [3] = (auc, total positives, total negatives) on the device."""
+    lib = _lib.load()
+    for nm, t in (("scores", scores), ("pos_w", pos_w), ("neg_w", neg_w)):
+        _cuda(t, nm, F32)
+    scores, pos_w, neg_w = scores.contiguous().reshape(-1), pos_w.contiguous().reshape(-1), neg_w.contiguous().reshape(-1)
+    if not (scores.numel() == pos_w.numel() == neg_w.numel()):
+        raise RuntimeError("lstc_vad_b200.weighted_auc: scores / pos_w / neg_w must have the same length")
+    out = torch.empty(3, device=scores.device, dtype=torch.float64)
+    st = lib.lstc_weighted_auc(_p(scores), _p(pos_w), _p(neg_w), scores.numel(), _p(out), _stream())
+    _lib.check(st, "lstc_weighted_auc")
+    LAUNCHES.add(1)
+    return out
+
+
 def threshold_labels(scores: torch.Tensor, thr: float) -> torch.Tensor:
     lib = _lib.load()
     _cuda(scores, "scores", F32)

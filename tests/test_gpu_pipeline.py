@@ -198,3 +198,26 @@ def test_ucf_bin_pooling_matches_oracle(n_clips):
     ref2, _ = O.pool_video_bins(feats, 32, False)
     got2, _ = pool_video_bins(feats.cuda(), 32, False)
     assert (got2.cpu() - ref2).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("n,ties", [(1, False), (37, False), (1000, True), (16384, True), (5000, False)])
+def test_gpu_frame_level_auc_matches_sklearn(n, ties):
+    from sklearn.metrics import auc, roc_curve
+    from lstc_vad_b200.harness import frame_level_auc
+    g = torch.Generator().manual_seed(n)
+    scores = torch.rand(n, generator=g)
+    if ties:
+        scores = (scores * 50).round() / 50  # many equal scores -> grouped ROC steps
+    frames = torch.randint(1, 4, (n,), generator=g) * 16
+    pos = (torch.rand(n, generator=g) < 0.3 + 0.4 * scores).float() * frames * torch.rand(n, generator=g).round()
+    pos = pos.round()
+    neg = frames - pos
+    if n == 1:
+        pos, neg = torch.tensor([16.0]), torch.tensor([16.0])
+    # sklearn on the expanded per-frame arrays, exactly as utils/eval_utils.py does
+    y = torch.cat([torch.cat([torch.ones(int(p)), torch.zeros(int(q))]) for p, q in zip(pos, neg)]).numpy()
+    s = torch.cat([torch.full((int(p + q),), float(v)) for v, p, q in zip(scores, pos, neg)]).numpy()
+    fpr, tpr, _ = roc_curve(y, s)
+    ref = auc(fpr, tpr)
+    got = frame_level_auc(scores.cuda(), pos, neg)
+    assert abs(got - ref) < 1e-9, (got, ref)
