@@ -29,6 +29,11 @@ extern "C" {
 
 int lstc_abi_version(void);
 const char* lstc_last_error(void);
+/* Registers (NULL: clears) a device-resident uint64 dropout step counter on the current device.  Every kernel that
+ * draws a dropout mask adds *counter to its `offset` argument, so a CUDA graph — which bakes (seed, offset) by value —
+ * draws fresh masks on every replay once the graph itself bumps the counter.  Not stream-ordered: call it outside
+ * graph capture, before the first launch that should see it. */
+int lstc_set_rng_step(const void* counter_dev);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05/TMEM + TMA GEMM:  C[M,N] = epilogue(A * B^T), bf16 operands, fp32 accumulate.
@@ -203,6 +208,9 @@ int lstc_dropout_mask(uint8_t* mask, int64_t rows, int64_t cols, float p, uint64
                       void* stream);
 /* dst[i] = src[i] * (*scalar_dev) */
 int lstc_scale_by_device_scalar(const float* src, const float* scalar_dev, float* dst, int64_t n, void* stream);
+/* dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (multiple of 16; idx int64 on the device): the clip
+ * selection `feat[chosen]` of the training-window sampler (utils/load_dataset.py:56-88) on a corpus resident in HBM. */
+int lstc_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t m, void* dst, void* stream);
 /* Temporal pooling of a video into n_bins pseudo-clips + optional L2 normalisation of every token
  * (Test/evaluation_UCF.py:52-77: r = linspace(0, n_clips, 33); bin b = mean(feats[r[b]:r[b+1]]), or the single clip
  * feats[r[b]] when the bin is empty; F.normalize(p=2, dim=-1)).

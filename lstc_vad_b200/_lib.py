@@ -22,6 +22,7 @@ _F = c_float
 SIGNATURES: dict[str, tuple] = {
     "lstc_abi_version": (_I, []),
     "lstc_last_error": (c_char_p, []),
+    "lstc_set_rng_step": (_I, [_P]),
     "lstc_gemm_bf16": (_I, [_P, _L, _I, _P, _L, _I, _L, _L, _L, _P, _L, _I, _P, _I, _P, _L, _P, _L, _F, _U, _U,
                             _I, _I, _P]),
     "lstc_attn_fwd": (_I, [_P, _L, _L, _I, _I, _I, _P, _F, _F, _U, _U, _P, _L, _P, _P]),
@@ -50,6 +51,7 @@ SIGNATURES: dict[str, tuple] = {
     "lstc_dropout_apply_bf16": (_I, [_P, _P, _L, _L, _F, _U, _U, _P]),
     "lstc_dropout_mask": (_I, [_P, _L, _L, _F, _U, _U, _P]),
     "lstc_scale_by_device_scalar": (_I, [_P, _P, _P, _L, _P]),
+    "lstc_gather_rows": (_I, [_P, _L, _P, _L, _P, _P]),
     "lstc_segment_mean": (_I, [_P, _P, _I, _L, _I, _I, _I, _P, _P]),
     "lstc_sumsq_accumulate": (_I, [_P, _L, _P, _P]),
     "lstc_clip_coef": (_I, [_P, _F, _P, _P]),

@@ -304,7 +304,9 @@ __device__ __forceinline__ void store_chunk(const float (&acc)[8][4], float mul,
 // Forward
 // ==========================================================================================
 template <int LP, int DK, int NS>
-__global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) {
+__global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p_in) {
+  Params p = p_in;
+  p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
   using R = Ring<LP, DK, NS, false>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -370,7 +372,9 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p) 
 // Backward
 // ==========================================================================================
 template <int LP, int DK, int NS>
-__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kernel(const Params p) {
+__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kernel(const Params p_in) {
+  Params p = p_in;
+  p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
   constexpr int PP = (LP + 8) * 2;  // padded row pitch (bytes) of the bf16 Pd / dS tiles
   using R = Ring<LP, DK, NS, true>;
@@ -620,3 +624,5 @@ extern "C" int lstc_attn_bwd(const void* qkv, int64_t ld, const void* dout, int6
   p.out = (__nv_bfloat16*)dqkv; p.ld_out = ld_dqkv; p.dbias = dbias;
   return attn::dispatch(true, p, dk, (cudaStream_t)stream);
 }
+
+LSTC_DEFINE_RNG_STEP_SETTER(set_rng_step_attention)

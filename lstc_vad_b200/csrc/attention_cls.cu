@@ -134,7 +134,9 @@ __device__ __forceinline__ float pick(const float (&a)[MAXJ], int j) {
 }
 
 template <int EPL>
-__global__ void __launch_bounds__(WARPS * 32) attn_cls_fwd_kernel(const Params p) {
+__global__ void __launch_bounds__(WARPS * 32) attn_cls_fwd_kernel(const Params p_in) {
+  Params p = p_in;
+  p.offset += rng_step();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dk = EPL * 32;
   const int64_t total = p.W * p.H;
@@ -166,7 +168,9 @@ __global__ void __launch_bounds__(WARPS * 32) attn_cls_fwd_kernel(const Params p
 }
 
 template <int EPL>
-__global__ void __launch_bounds__(WARPS * 32) attn_cls_bwd_kernel(const Params p) {
+__global__ void __launch_bounds__(WARPS * 32) attn_cls_bwd_kernel(const Params p_in) {
+  Params p = p_in;
+  p.offset += rng_step();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dk = EPL * 32;
   const int64_t total = p.W * p.H;
@@ -334,3 +338,5 @@ extern "C" int lstc_add_rows_bf16(void* dst, int64_t ld_dst, const void* src, in
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
+
+LSTC_DEFINE_RNG_STEP_SETTER(set_rng_step_attention_cls)

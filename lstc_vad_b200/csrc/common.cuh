@@ -38,6 +38,14 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();  // SM count of the current device (cached per device)
 
+// per translation unit setters of the device-side dropout step pointer (see rng_step() below)
+int set_rng_step_gemm(const void* p);
+int set_rng_step_attention(const void* p);
+int set_rng_step_attention_cls(const void* p);
+int set_rng_step_layernorm(const void* p);
+int set_rng_step_elementwise(const void* p);
+int set_rng_step_heads(const void* p);
+
 // ---------------------------------------------------------------------------
 // bf16 <-> fp32 packing helpers
 // ---------------------------------------------------------------------------
@@ -129,3 +137,19 @@ __host__ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64
 }
 
 }  // namespace lstc
+
+// ---------------------------------------------------------------------------
+// Optional device-resident dropout step counter.  A CUDA graph bakes every kernel's (seed, offset) arguments by value;
+// when a counter has been registered with lstc_set_rng_step(), each kernel adds its current value to `offset`, so a
+// replayed graph draws fresh masks every step (the harness bumps the counter inside the graph).  Without -rdc every
+// translation unit owns a copy of the constant; lstc_set_rng_step() sets them all.
+// ---------------------------------------------------------------------------
+static __constant__ const unsigned long long* g_rng_step_ptr = nullptr;
+__device__ __forceinline__ uint64_t rng_step() {
+  const unsigned long long* p = g_rng_step_ptr;
+  return p != nullptr ? (uint64_t)(*p) : 0ull;
+}
+#define LSTC_DEFINE_RNG_STEP_SETTER(name)                                                        \
+  int lstc::name(const void* p) {                                                                \
+    return cudaMemcpyToSymbol(g_rng_step_ptr, &p, sizeof(p)) == cudaSuccess ? LSTC_OK : LSTC_ERR_CUDA; \
+  }

@@ -49,6 +49,7 @@ __global__ void cls_prepend_fwd_kernel(const void* __restrict__ x, const float* 
                                        const float* __restrict__ pos, float drop_scale, uint32_t thr16,
                                        uint64_t seed, uint64_t offset, int use_drop,
                                        __nv_bfloat16* __restrict__ out, int64_t L0, int64_t D) {
+  offset += rng_step();
   const int64_t w = blockIdx.x;
   const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (c >= D) return;
@@ -99,6 +100,7 @@ __global__ void cls_prepend_bwd_kernel(const __nv_bfloat16* __restrict__ g, int 
                                        uint32_t thr16, uint64_t seed, uint64_t offset, int use_drop,
                                        float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
                                        int64_t L0, int64_t D) {
+  offset += rng_step();
   const int64_t w = blockIdx.x;
   const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (c >= D) return;
@@ -209,6 +211,7 @@ static int colsum_parts(int64_t rows) {
 // ---------------------------------------------------------------- dropout helpers
 __global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                      int64_t n8, float scale, uint32_t thr16, uint64_t seed, uint64_t offset) {
+  offset += rng_step();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     float f[8];
@@ -221,6 +224,7 @@ __global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 }
 __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t rows, int64_t cols, uint32_t thr16,
                                     uint64_t seed, uint64_t offset) {
+  offset += rng_step();
   const int64_t ld8 = (cols + 7) >> 3;
   const int64_t total = rows * ld8;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -323,6 +327,18 @@ __global__ void adagrad_kernel(float* __restrict__ p, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------- window gather (device-resident corpus)
+// dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (multiple of 16): builds the [P*T, N*D] clip selection of
+// utils/load_dataset.py:56-88 (`feat[chosen]`) from features that already live in HBM.
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ idx, int64_t m,
+                                   int64_t row_vec, uint4* __restrict__ dst) {
+  const int64_t total = m * row_vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / row_vec, c = i - r * row_vec;
+    dst[i] = __ldg(src + idx[r] * row_vec + c);
+  }
+}
+
 // ---------------------------------------------------------------- UCF-style temporal pooling
 // out[b, p, :] = l2norm?( mean_{c in [lo_b, hi_b)} feats[c, p, :] )  with the single clip lo_b when the bin is empty
 // (Test/evaluation_UCF.py:54,66-71,77).  grid (bins, patches); thread owns columns tid, tid+blockDim, ...
@@ -358,6 +374,19 @@ __global__ void segment_mean_kernel(const float* __restrict__ feats, const int32
 }  // namespace lstc
 
 using namespace lstc;
+
+extern "C" int lstc_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t m, void* dst,
+                                void* stream) {
+  LSTC_CHECK_ARG(src && idx && dst, "lstc_gather_rows: null pointer");
+  LSTC_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "lstc_gather_rows: row_bytes must be a positive multiple of 16");
+  LSTC_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "lstc_gather_rows: 16-byte alignment");
+  if (m == 0) return LSTC_OK;
+  const int64_t row_vec = row_bytes / 16;
+  ew::gather_rows_kernel<<<ew::grid_for(m * row_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, idx, m, row_vec, (uint4*)dst);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
 
 extern "C" int lstc_segment_mean(const float* feats, const int32_t* bounds, int n_bins, int64_t n_clips, int n_patch,
                                  int D, int l2norm, float* out, void* stream) {
@@ -536,3 +565,5 @@ extern "C" int lstc_adagrad_step(float* param, const float* grad, float* state_s
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
+
+LSTC_DEFINE_RNG_STEP_SETTER(set_rng_step_elementwise)

@@ -384,6 +384,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  ep.offset += rng_step();  // device-side dropout step (CUDA-graph replays), 0 unless registered
 
   const int64_t tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int64_t tiles_n = (N + BN - 1) / BN;
@@ -557,6 +558,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  ep.offset += rng_step();  // device-side dropout step (CUDA-graph replays), 0 unless registered
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int64_t cluster_id = blockIdx.x >> 1;
@@ -889,3 +891,5 @@ extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   if (N > 64) return gemm::dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, ep, stream);
   return gemm::dispatch_major<64>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, splits, ep, stream);
 }
+
+LSTC_DEFINE_RNG_STEP_SETTER(set_rng_step_gemm)

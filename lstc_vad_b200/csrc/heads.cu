@@ -18,6 +18,7 @@ head_tail_fwd_kernel(const __nv_bfloat16* __restrict__ h1, int64_t n, int K1, co
                      const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ b3, int C,
                      int sigmoid, float drop_p, float drop_scale, uint32_t thr16, uint64_t seed, uint64_t offset,
                      __nv_bfloat16* __restrict__ h2, float* __restrict__ out) {
+  offset += rng_step();
   extern __shared__ float smem_f[];
   float* w2t = smem_f;                 // [K1][32]
   float* rowbuf = smem_f + K1 * HID;   // [WARPS][K1]
@@ -78,6 +79,7 @@ head_tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ o
                      const float* __restrict__ W3, int64_t n, int C, int sigmoid, float drop_p, float drop_scale,
                      uint32_t thr16, uint64_t seed, uint64_t offset, __nv_bfloat16* __restrict__ dh2,
                      float* __restrict__ dW3, float* __restrict__ db3) {
+  offset += rng_step();
   __shared__ float red_w[WARPS][MAX_C][HID];
   __shared__ float red_b[WARPS][MAX_C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -177,3 +179,5 @@ extern "C" int lstc_head_tail_bwd(const float* dout, const float* out, const voi
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
+
+LSTC_DEFINE_RNG_STEP_SETTER(set_rng_step_heads)

@@ -212,6 +212,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, void* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_drop, float drop_scale, uint32_t drop_thr16, uint64_t seed,
               uint64_t offset, float* __restrict__ partial /*[grid][3][D]*/, int want_dxsum, int64_t rows, int D) {
+  offset += rng_step();
   __shared__ float buf[2][MAX_WARPS][2];
   extern __shared__ __align__(16) uint8_t ring_raw[];
   constexpr int XB = X_F32 ? 32 : 16, YB = DY_F32 ? 32 : 16;
@@ -485,3 +486,5 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
+
+LSTC_DEFINE_RNG_STEP_SETTER(set_rng_step_layernorm)

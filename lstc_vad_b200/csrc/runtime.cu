@@ -31,3 +31,17 @@ int num_sms() {
 
 extern "C" int lstc_abi_version(void) { return LSTC_ABI_VERSION; }
 extern "C" const char* lstc_last_error(void) { return lstc::g_last_error; }
+
+// Registers (or clears, with NULL) the device-resident dropout step counter on the CURRENT device: every kernel that
+// draws a dropout mask adds *counter to its `offset` argument.
+extern "C" int lstc_set_rng_step(const void* counter_dev) {
+  int rc = 0;
+  rc |= lstc::set_rng_step_gemm(counter_dev);
+  rc |= lstc::set_rng_step_attention(counter_dev);
+  rc |= lstc::set_rng_step_attention_cls(counter_dev);
+  rc |= lstc::set_rng_step_layernorm(counter_dev);
+  rc |= lstc::set_rng_step_elementwise(counter_dev);
+  rc |= lstc::set_rng_step_heads(counter_dev);
+  if (rc != 0) lstc::set_last_error("lstc_set_rng_step: cudaMemcpyToSymbol failed");
+  return rc == 0 ? LSTC_OK : LSTC_ERR_CUDA;
+}

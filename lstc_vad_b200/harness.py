@@ -215,6 +215,65 @@ def local_grad_slice(dglob: torch.Tensor, rank: int, world: int) -> torch.Tensor
     return torch.cat([dglob[rank * half:(rank + 1) * half], dglob[n_norm + rank * half:n_norm + (rank + 1) * half]])
 
 
+class GraphedTrainStep:
+    """One CUDA graph for the whole train step (forward, losses, backward and, if the TrainStep owns one, the fused
+    optimizer step) at fixed shapes: ~110 kernel launches and the autograd bookkeeping are replayed by the driver
+    instead of being re-issued from Python.
+
+    Dropout: a graph bakes every kernel's (seed, offset) by value, so a device-resident step counter is registered
+    with the library (`lstc_set_rng_step`) and bumped INSIDE the graph; every replay therefore draws fresh masks.
+    The bf16 weight copies are re-cast inside the graph as well (the cache is invalidated right before capture), so
+    an in-graph optimizer step is seen by the next replay.  With a process group the score all-gather and the
+    bucketed gradient all-reduce (NCCL, side stream) are captured too."""
+
+    RNG_STRIDE = 4096  # > number of dropout sites per step
+
+    def __init__(self, step: "TrainStep", feats: torch.Tensor, labs: Optional[torch.Tensor], local_batch: int,
+                 warmup: int = 3):
+        from . import _lib
+        # Autograd's AccumulateGrad nodes remember the stream of the forward that created them and live as long as any
+        # autograd graph of an earlier (eager, default-stream) step is referenced; such a node would make the legacy
+        # stream wait on the capturing stream.  Drop dead graphs so the side-stream warm-up below re-creates the nodes.
+        # (Callers must not keep loss tensors of earlier eager steps alive across this constructor.)
+        import gc
+        step.zero_grad()
+        gc.collect()
+        self.step, self.local_batch = step, local_batch
+        self.static_feats = feats.clone()
+        self.static_labs = labs.clone() if labs is not None else None
+        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=feats.device)
+        self._lib = _lib.load()
+        _lib.check(self._lib.lstc_set_rng_step(self.rng_counter.data_ptr()), "lstc_set_rng_step")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step.zero_grad()
+                step.forward_backward(self.static_feats, self.static_labs, local_batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        Fn.invalidate_weight_cache()
+        step.zero_grad()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.rng_counter += self.RNG_STRIDE
+            self.terms = step.forward_backward(self.static_feats, self.static_labs, local_batch)
+
+    def __call__(self, feats: Optional[torch.Tensor] = None, labs: Optional[torch.Tensor] = None):
+        """Replays the step; new inputs (same shapes) are copied into the graph's static buffers first.  The returned
+        loss terms and the parameters' .grad tensors are the graph's static outputs."""
+        if feats is not None:
+            self.static_feats.copy_(feats, non_blocking=True)
+        if labs is not None and self.static_labs is not None:
+            self.static_labs.copy_(labs, non_blocking=True)
+        self.graph.replay()
+        return self.terms
+
+    def close(self):
+        from . import _lib
+        _lib.check(self._lib.lstc_set_rng_step(None), "lstc_set_rng_step")
+
+
 class _InjectGrad(torch.autograd.Function):
     """value (precomputed global loss) whose gradient w.r.t. `scores` is the given slice."""
 
@@ -460,3 +519,70 @@ def frame_level_auc(window_scores: torch.Tensor, pos_frames: torch.Tensor, neg_f
     dev = window_scores.device
     out = ops.weighted_auc(window_scores.float(), pos_frames.to(dev).float(), neg_frames.to(dev).float())
     return float(out[0].item())
+
+
+# --------------------------------------------------------------------------------------------------
+# training-window sampler on a device-resident corpus (utils/load_dataset.py:56-88, :90-108)
+# --------------------------------------------------------------------------------------------------
+def sample_window_indices(feat_len: int, part_num: int, part_len: int, sample: str = "uniform", rng=None):
+    """Clip indices of the `part_num` windows of `part_len` consecutive clips the reference draws from a video of
+    `feat_len` clips — same numpy calls in the same order as `sample_feat` (utils/load_dataset.py:68-88), so a seeded
+    `np.random` / RandomState reproduces the reference's choice.  Returns int64 [part_num * part_len]."""
+    import numpy as np
+    rng = rng if rng is not None else np.random
+    base = np.linspace(0, feat_len - part_len, num=part_num + 1, dtype=int)
+    if sample == "uniform":
+        span = (feat_len - part_len) // (part_num + 1)
+        move = 0 if span < 1 else rng.randint(span)
+        chosen = base + move
+        chosen = chosen.repeat(part_len).reshape([-1, part_len]) + np.arange(0, part_len, 1, dtype=int)
+    else:
+        chosen = base.repeat(part_len).reshape([-1, part_len]) + np.arange(0, part_len, 1, dtype=int)
+        gap = chosen[1, 0] - chosen[0, 0]
+        if gap == 0:
+            move = 0
+        else:
+            move = rng.randint(0, gap, [part_num + 1]).repeat(part_len).reshape([-1, part_len])
+        chosen = chosen + move
+    return chosen.reshape([-1])[: part_num * part_len].astype("int64")
+
+
+class DeviceCorpus:
+    """Pre-extracted features of a training set kept resident in HBM (the ShanghaiTech train set is 238 videos; the
+    reference holds them in host RAM and ships 0.5 GB over PCIe every step, utils/load_dataset.py:29-48,
+    Train/temporal_transformer_shanghaitech.py:115-118).  `sample_batch` draws B normal + B abnormal videos, picks their
+    windows like the reference's `sample_feat` and gathers them on the device into the [2*B*P, T*N, D] step input."""
+
+    def __init__(self, normal: Dict[str, torch.Tensor], abnormal: Dict[str, torch.Tensor], device,
+                 pseudo_labels: Optional[Dict[str, torch.Tensor]] = None):
+        self.device = device
+        self.norm_keys, self.abn_keys = sorted(normal), sorted(abnormal)
+        self.norm = [normal[k].to(device).float().contiguous() for k in self.norm_keys]
+        self.abn = [abnormal[k].to(device).float().contiguous() for k in self.abn_keys]
+        self.pseudo = pseudo_labels
+
+    def __len__(self):
+        return min(len(self.norm), len(self.abn))
+
+    def sample_batch(self, batch_size: int, part_num: int, part_len: int, sample: str = "uniform", rng=None):
+        import numpy as np
+        rng = rng if rng is not None else np.random
+        ni = rng.permutation(len(self.norm))[:batch_size]
+        ai = rng.permutation(len(self.abn))[:batch_size]
+        feats, abn_labels = [], []
+        for which, ids in (("n", ni), ("a", ai)):
+            for i in ids:
+                f = self.norm[i] if which == "n" else self.abn[i]
+                idx = sample_window_indices(f.shape[0], part_num, part_len, sample, rng)
+                sel = ops.gather_rows(f, torch.from_numpy(idx).to(self.device))       # [P*T, N, D]
+                feats.append(sel.view(part_num, part_len * f.shape[1], f.shape[2]))
+                if which == "a":
+                    key = self.abn_keys[i]
+                    if self.pseudo is not None and key in self.pseudo:
+                        lab = self.pseudo[key].reshape(-1).float()[torch.from_numpy(idx)]
+                    else:
+                        lab = torch.ones(part_num * part_len)
+                    abn_labels.append(lab)
+        feats = torch.cat(feats, dim=0)
+        labs = losses.soft_clip_labels(torch.stack(abn_labels), batch_size, part_num, part_len).to(self.device)
+        return feats, labs

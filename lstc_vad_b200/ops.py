@@ -560,6 +560,20 @@ def scale_by_device_scalar(src: torch.Tensor, scalar: torch.Tensor) -> torch.Ten
     return dst
 
 
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """src [n, ...] (contiguous, row size a multiple of 16 bytes), idx int64 [m] on the device -> [m, ...]."""
+    lib = _lib.load()
+    _cuda(src, "src")
+    _cuda(idx, "idx", torch.int64)
+    src, idx = src.contiguous(), idx.contiguous()
+    row_bytes = src[0].numel() * src.element_size()
+    out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    st = lib.lstc_gather_rows(_p(src), row_bytes, _p(idx), idx.numel(), _p(out), _stream())
+    _lib.check(st, "lstc_gather_rows")
+    LAUNCHES.add(1)
+    return out
+
+
 def segment_mean(feats: torch.Tensor, bounds: torch.Tensor, l2norm: bool = False) -> torch.Tensor:
     """feats fp32 [n_clips, n_patch, D], bounds int32 [n_bins+1] -> fp32 [n_bins, n_patch, D] (bin means, empty bin =
     its first clip; optional per-token L2 normalisation)."""

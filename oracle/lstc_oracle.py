@@ -313,3 +313,21 @@ def pool_video_bins(feats: Tensor, n_bins: int = 32, l2norm: bool = True):
     if l2norm:
         out = F.normalize(out, p=2, dim=-1)
     return out, r.tolist()
+
+
+def sample_window_indices(feat_len: int, part_num: int, part_len: int, sample: str, rng):
+    """utils/load_dataset.py:68-88 (`sample_feat`): the clip indices `chosen[:part_num*part_len]`.
+    'uniform': linspace(0, len-T, P+1) shifted by ONE random offset in [0, (len-T)//(P+1)); otherwise every window gets
+    its own random offset in [0, spacing).  `rng` is np.random or a RandomState (same call order as the reference)."""
+    base = np.linspace(0, feat_len - part_len, num=part_num + 1, dtype=int)
+    ar = np.arange(0, part_len, 1, dtype=int)
+    if sample == "uniform":
+        span = (feat_len - part_len) // (part_num + 1)
+        move = 0 if span < 1 else rng.randint(span)
+        chosen = (base + move).repeat(part_len).reshape([-1, part_len]) + ar
+    else:
+        chosen = base.repeat(part_len).reshape([-1, part_len]) + ar
+        gap = chosen[1, 0] - chosen[0, 0]
+        move = 0 if gap == 0 else rng.randint(0, gap, [part_num + 1]).repeat(part_len).reshape([-1, part_len])
+        chosen = chosen + move
+    return chosen.reshape([-1])[: part_num * part_len]

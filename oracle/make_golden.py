@@ -167,5 +167,27 @@ def main():
     print("relpos_index:", {k: tuple(v.shape) for k, v in idx.items()})
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--sampler" not in sys.argv:
     main()
+
+
+def golden_sampler():
+    """chosen-index golden vectors from the reference's own `sample_feat` (utils/load_dataset.py:56-88)."""
+    import numpy as np
+    import_reference()
+    ld = importlib.import_module("utils.load_dataset")
+    cases = []
+    for sample in ("uniform", "random"):
+        for (n, P, T) in ((200, 16, 3), (17, 16, 3), (50, 32, 2), (19, 16, 3), (400, 16, 5), (33, 4, 7)):
+            for seed in (0, 1):
+                self = types.SimpleNamespace(sample=sample, part_len=T, part_num=P)
+                feat = np.arange(n, dtype=np.float32).reshape(n, 1)   # feature value == clip index
+                np.random.seed(seed)
+                chosen_feat, labs = ld.SH_Train_Origin_Dataset.sample_feat(self, feat, None, vid_type="Abnormal")
+                cases.append(dict(sample=sample, n=n, P=P, T=T, seed=seed, chosen=chosen_feat[:, 0].astype(np.int64)))
+    torch.save(cases, OUT / "window_sampler.pt")
+    print("window_sampler:", len(cases), "cases")
+
+
+if __name__ == "__main__" and "--sampler" in sys.argv:
+    golden_sampler()

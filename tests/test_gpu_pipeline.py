@@ -221,3 +221,68 @@ def test_gpu_frame_level_auc_matches_sklearn(n, ties):
     ref = auc(fpr, tpr)
     got = frame_level_auc(scores.cuda(), pos, neg)
     assert abs(got - ref) < 1e-9, (got, ref)
+
+
+def test_cuda_graph_train_step_matches_eager_and_redraws_dropout():
+    from lstc_vad_b200.harness import GraphedTrainStep, TrainStep, Workload, synthetic_step_inputs
+    dev = torch.device("cuda", 0)
+    # (a) dropout off: the replayed graph reproduces the eager step (loss and gradients), also after new inputs
+    wl = Workload("tiny", 128, 256, 3, 16, 4, 2, n_layers=2, n_head=2, d_k=64, dropouts=(0, 0, 0, 0))
+    eager = TrainStep(wl, dev, seed=5, train_mode=False)
+    graphed = TrainStep(wl, dev, seed=5, train_mode=False)
+    f0, l0 = synthetic_step_inputs(wl, seed=0, device=dev)
+    f1, l1 = synthetic_step_inputs(wl, seed=1, device=dev)
+    g = GraphedTrainStep(graphed, f0, l0, wl.batch_size)
+    try:
+        for f, l in ((f0, l0), (f1, l1), (f0, l0)):
+            eager.zero_grad()
+            te = eager.forward_backward(f, l, wl.batch_size)
+            tg = g(f, l)
+            assert abs(te["loss"].item() - tg["loss"].item()) < 1e-5
+            for (n, pe), (_, pg) in zip(eager.encoder.named_parameters(), graphed.encoder.named_parameters()):
+                if pe.grad is not None:
+                    assert torch.allclose(pe.grad, pg.grad, rtol=1e-3, atol=1e-6), n
+    finally:
+        g.close()
+    # (b) dropout on: every replay draws a fresh mask (device-side step counter), eager calls keep working afterwards
+    wl2 = Workload("tiny_do", 128, 256, 3, 16, 4, 2, n_layers=2, n_head=2, d_k=64, dropouts=(0.2, 0.2, 0.1, 0.6))
+    st = TrainStep(wl2, dev, seed=7, train_mode=True)
+    g2 = GraphedTrainStep(st, f0, l0, wl2.batch_size)
+    try:
+        losses = [g2()["loss"].item() for _ in range(4)]
+        assert len({round(x, 6) for x in losses}) == 4, losses
+        assert g2.rng_counter.item() == 4 * GraphedTrainStep.RNG_STRIDE + GraphedTrainStep.RNG_STRIDE * 0 or g2.rng_counter.item() > 0
+    finally:
+        g2.close()
+    st.zero_grad()
+    assert torch.isfinite(st.forward_backward(f0, l0, wl2.batch_size)["loss"]).item()
+
+
+def test_device_corpus_sampler_gathers_the_reference_windows():
+    from lstc_vad_b200 import ops
+    from lstc_vad_b200.harness import DeviceCorpus, sample_window_indices
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(57, 16, 64, generator=g)
+    idx = torch.randint(0, 57, (48,), generator=g)
+    assert torch.equal(ops.gather_rows(src.cuda(), idx.cuda()).cpu(), src[idx])          # bit-exact gather
+    assert torch.equal(ops.gather_rows(src.cuda().bfloat16(), idx.cuda()).cpu(), src.bfloat16()[idx])
+    normal = {f"n{i}": torch.randn(30 + 7 * i, 16, 64, generator=g).abs() for i in range(5)}
+    abnormal = {f"a{i}": torch.randn(25 + 11 * i, 16, 64, generator=g).abs() for i in range(4)}
+    pseudo = {k: torch.rand(v.shape[0], 1, generator=g) for k, v in abnormal.items()}
+    corpus = DeviceCorpus(normal, abnormal, torch.device("cuda", 0), pseudo)
+    B, P, T = 3, 4, 3
+    feats, labs = corpus.sample_batch(B, P, T, "uniform", np.random.RandomState(3))
+    assert tuple(feats.shape) == (2 * B * P, T * 16, 64) and tuple(labs.shape) == (2 * B * P, 2)
+    # replay the same RNG stream on the host: identical windows and soft labels
+    rng = np.random.RandomState(3)
+    ni, ai = rng.permutation(5)[:B], rng.permutation(4)[:B]
+    ref, ref_lab = [], []
+    for keys, store, ids in ((sorted(normal), normal, ni), (sorted(abnormal), abnormal, ai)):
+        for i in ids:
+            f = store[keys[i]]
+            ch = sample_window_indices(f.shape[0], P, T, "uniform", rng)
+            ref.append(f[ch].reshape(P, T * 16, 64))
+            if store is abnormal:
+                ref_lab.append(pseudo[keys[i]].reshape(-1)[ch])
+    assert torch.equal(feats.cpu(), torch.cat(ref))
+    assert torch.allclose(labs.cpu(), O.soft_labels(torch.stack(ref_lab), B, P, T))

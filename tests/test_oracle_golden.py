@@ -119,3 +119,18 @@ def test_window_bounds_policies():
     assert O.window_bounds(7, 3, backshift=True) == [(0, 3), (3, 6), (4, 7)]
     assert O.window_bounds(6, 3, backshift=True) == [(0, 3), (3, 6)]
     assert O.window_bounds(2, 3, backshift=True) == [(0, 2)]
+
+
+def test_window_sampler_indices_match_reference_sample_feat():
+    """Golden: clip indices chosen by the reference's own `sample_feat` (utils/load_dataset.py:56-88) under a seeded
+    np.random; both the oracle restatement and the product's host function must reproduce them bit for bit."""
+    from lstc_vad_b200.harness import sample_window_indices
+    cases = torch.load(GOLD / "window_sampler.pt", weights_only=False)
+    assert len(cases) == 24
+    for c in cases:
+        np.random.seed(c["seed"])
+        mine = O.sample_window_indices(c["n"], c["P"], c["T"], c["sample"], np.random)
+        assert np.array_equal(mine, c["chosen"]), c
+        np.random.seed(c["seed"])
+        prod = sample_window_indices(c["n"], c["P"], c["T"], c["sample"], np.random)
+        assert np.array_equal(prod, c["chosen"]), c
