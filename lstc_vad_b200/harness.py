@@ -223,14 +223,18 @@ class GraphedTrainStep:
     Dropout: a graph bakes every kernel's (seed, offset) by value, so a device-resident step counter is registered
     with the library (`lstc_set_rng_step`) and bumped INSIDE the graph; every replay therefore draws fresh masks.
     The bf16 weight copies are re-cast inside the graph as well (the cache is invalidated right before capture), so
-    an in-graph optimizer step is seen by the next replay.  With a process group the score all-gather and the
-    bucketed gradient all-reduce (NCCL, side stream) are captured too."""
+    an in-graph optimizer step is seen by the next replay.  Single-GPU only (the bucketed all-reduce of the
+    data-parallel path stays eager)."""
 
     RNG_STRIDE = 4096  # > number of dropout sites per step
 
     def __init__(self, step: "TrainStep", feats: torch.Tensor, labs: Optional[torch.Tensor], local_batch: int,
                  warmup: int = 3):
         from . import _lib
+        if step.world != 1:
+            # capturing the NCCL side-stream all-reduce works but gains ~1 % and process-group teardown after a
+            # captured collective hung in testing: the data-parallel path stays eager
+            raise RuntimeError("GraphedTrainStep supports world_size 1 only")
         # Autograd's AccumulateGrad nodes remember the stream of the forward that created them and live as long as any
         # autograd graph of an earlier (eager, default-stream) step is referenced; such a node would make the legacy
         # stream wait on the capturing stream.  Drop dead graphs so the side-stream warm-up below re-creates the nodes.
