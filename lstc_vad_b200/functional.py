@@ -375,6 +375,7 @@ class MHAClsFn(torch.autograd.Function):
 class FFNConfig:
     layer_norm: bool
     drop: tuple
+    out_f32: bool = False   # last block of the encoder: the LayerNorm writes the caller's fp32 output directly
 
 
 class FFNBlockFn(torch.autograd.Function):
@@ -393,7 +394,7 @@ class FFNBlockFn(torch.autograd.Function):
         h = ops.gemm(x2, w1_16, bias=b1p, relu=True)                                    # [M, Dh+pad]
         y2 = ops.gemm(h, w2_16, bias=b2.detach().contiguous(), dropout=cfg.drop, residual=x2)
         if cfg.layer_norm:
-            out, mean, rstd = ops.layernorm_fwd(y2, ln_w.detach(), ln_b.detach(), 1e-6, BF16)
+            out, mean, rstd = ops.layernorm_fwd(y2, ln_w.detach(), ln_b.detach(), 1e-6, F32 if cfg.out_f32 else BF16)
         else:
             out, mean, rstd = y2, None, None
         ctx.cfg, ctx.shape, ctx.pad = cfg, shape, pad

@@ -85,13 +85,17 @@ class Encoder(nn.Module):
         x = self._embed(enc_output)
 
         attn_list, v_list = [], []
-        for enc_layer in self.layer_stack:
-            x, attn, v = enc_layer._forward_bf16(x, return_attn, return_attn_v)
+        want_f32 = in_dtype != BF16
+        n_layers = len(self.layer_stack)
+        for li, enc_layer in enumerate(self.layer_stack):
+            # the last block's LayerNorm writes the caller's fp32 output directly (no separate cast pass)
+            x, attn, v = enc_layer._forward_bf16(x, return_attn, return_attn_v,
+                                                 out_f32=want_f32 and li == n_layers - 1)
             if return_attn or return_attn_v:
                 attn_list.append(attn)
             if return_attn_v:
                 v_list.append(v)
-        out = like_input(x, BF16 if in_dtype == BF16 else torch.float32)
+        out = x if (want_f32 and x.dtype == torch.float32) else like_input(x, BF16 if in_dtype == BF16 else torch.float32)
         if return_attn_v == True:  # noqa: E712
             return out, attn_list, v_list
         if return_attn:

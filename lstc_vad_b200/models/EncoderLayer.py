@@ -21,10 +21,10 @@ class EncoderLayer(nn.Module):
         self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=FFN_dropout, layerNorm=FFN_layerNorm)
         self.FFN_need = FFN_need
 
-    def _forward_bf16(self, x, return_attn=False, return_attn_v=False):
+    def _forward_bf16(self, x, return_attn=False, return_attn_v=False, out_f32=False):
         out, attn, v = self.slf_attn._forward_bf16(x, return_attn, return_attn_v)
         if self.FFN_need == True:  # noqa: E712
-            out = self.pos_ffn._forward_bf16(out)
+            out = self.pos_ffn._forward_bf16(out, out_f32=out_f32)
         return out, attn, v
 
     def _forward_cls_bf16(self, x):

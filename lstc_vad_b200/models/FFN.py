@@ -18,9 +18,11 @@ class PositionwiseFeedForward(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.layerNorm_flag = layerNorm
 
-    def _forward_bf16(self, x):
+    def _forward_bf16(self, x, out_f32=False):
+        """x bf16 -> bf16, or fp32 when `out_f32` and the block ends in its LayerNorm (which then writes fp32)."""
         cfg = Fn.FFNConfig(layer_norm=self.layerNorm_flag == True,  # noqa: E712 (reference compares with ==)
-                           drop=Fn.next_dropout(self.dropout.p, self.training))
+                           drop=Fn.next_dropout(self.dropout.p, self.training),
+                           out_f32=bool(out_f32) and self.layerNorm_flag == True)  # noqa: E712
         return Fn.FFNBlockFn.apply(x, self.w_1.weight, self.w_1.bias, self.w_2.weight, self.w_2.bias,
                                    self.layer_norm.weight, self.layer_norm.bias, cfg)
 
