@@ -13,7 +13,7 @@
  *   - bf16 tensors are passed as `void*` (raw __nv_bfloat16), fp32 as `float*`;
  *   - every function returns 0 on success or a LSTC_ERR_* code; `lstc_last_error()` returns a
  *     thread-local human-readable message for the last failure.  Nothing falls back to the CPU.
- *   - dropout masks are a pure function of (seed, offset, element index) — Philox4x32-10, 16 random
+ *   - dropout masks are a pure function of (seed, offset, element index) — Philox4x32-7, 16 random
  *     bits per element — so backward kernels regenerate the forward mask instead of loading it.
  */
 #ifndef LSTC_VAD_B200_H_

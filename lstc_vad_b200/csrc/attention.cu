@@ -53,6 +53,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -84,16 +89,35 @@ struct Params {
   float* dbias;  // bwd optional
 };
 
-// cp.async of one [L x 64] column chunk starting at `src` (row pitch ld elements); rows L..LP-1 are zero-filled
+// Per-thread copy pattern of a [LP x 64] chunk tile: the CTA's LP*2 threads move LP*8 16-byte pieces, i.e. every
+// thread moves exactly 4 -- column piece c16 = tid & 7 of rows r0 + k*LP/4 (k = 0..3, r0 = tid >> 3).  Everything
+// that does not depend on the tile (shared-memory offsets, validity of the 4 rows, the row step) is computed once
+// per kernel, so issuing a tile costs ~4 instructions per cp.async instead of re-deriving row / column / swizzle /
+// 64-bit address per piece.  Rows L..LP-1 are zero-filled (src-size 0).
 template <int LP>
-__device__ __forceinline__ void load_chunk_tile(uint32_t s_tile, const __nv_bfloat16* src, int64_t ld, int L) {
-  for (int idx = threadIdx.x; idx < LP * 8; idx += LP * 2 /* = blockDim.x */) {
-    const int r = idx >> 3, c = idx & 7;
-    const bool valid = r < L;
-    cp_async16(s_tile + ct_off(r, c), valid ? (const void*)(src + (int64_t)r * ld + c * 8) : (const void*)src,
-               valid ? 16 : 0);
+struct TileCopy {
+  static constexpr int RSTEP = LP / 4;
+  uint32_t dst[4];  // byte offsets inside a tile
+  int nvalid;       // pieces k < nvalid lie in rows < L
+
+  __device__ __forceinline__ void init(int L) {
+    const int r0 = threadIdx.x >> 3, c16 = threadIdx.x & 7;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = ct_off(r0 + k * RSTEP, c16);
+    nvalid = L > r0 ? (L - r0 + RSTEP - 1) / RSTEP : 0;
+    if (nvalid > 4) nvalid = 4;
   }
-}
+  // `src` = this thread's first piece (row r0, column piece c16 of the chunk); `kstep` = RSTEP rows in elements;
+  // `safe` = any valid global address (used for the zero-filled pieces)
+  __device__ __forceinline__ void load(uint32_t s_tile, const __nv_bfloat16* src, int64_t kstep,
+                                       const __nv_bfloat16* safe) const {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool v = k < nvalid;
+      cp_async16(s_tile + dst[k], v ? (const void*)(src + k * kstep) : (const void*)safe, v ? 16 : 0);
+    }
+  }
+};
 
 // acc (this warp's 16 rows x LP) += A_c[m0.., 0:64] * B_c[:, 0:64]^T, both chunk tiles [rows][64] (k contiguous)
 template <int LP>
@@ -140,21 +164,35 @@ __device__ __forceinline__ void softmax_dropout(float (&s)[LP / 8][4], uint32_t 
                                                 int h, int m0, int lane) {
   const int g = lane >> 2, t = lane & 3;
   constexpr float LOG2E = 1.4426950408889634f;
+  const float sl2 = p.scale * LOG2E;  // scores are taken to the log2 domain in the same FFMA that scales them
+  const int nfull = p.L >> 3;         // n-tiles whose 8 columns are all real keys (warp-uniform)
+  const bool has_bias = p.bias != nullptr;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = m0 + g + 8 * r;
-    const float* brow = (p.bias != nullptr && row < p.L) ? p.bias + ((int64_t)h * p.L + row) * p.L : nullptr;
+    // rows >= L are padding (never stored): they read the last real row's bias so the address stays valid
+    const float* brow = has_bias ? p.bias + ((int64_t)h * p.L + (row < p.L ? row : p.L - 1)) * p.L + 2 * t : nullptr;
     float mx = -INFINITY;
 #pragma unroll
     for (int n = 0; n < LP / 8; ++n) {
+      if (n < nfull) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = n * 8 + 2 * t + e;
-        float v = s[n][2 * r + e] * p.scale;
-        if (brow != nullptr && col < p.L) v += __ldg(brow + col);
-        v = col < p.L ? v : -INFINITY;
-        s[n][2 * r + e] = v;
-        mx = fmaxf(mx, v);
+        for (int e = 0; e < 2; ++e) {
+          float v = s[n][2 * r + e] * sl2;
+          if (has_bias) v = fmaf(__ldg(brow + n * 8 + e), LOG2E, v);
+          s[n][2 * r + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n * 8 + 2 * t + e;
+          float v = s[n][2 * r + e] * sl2;
+          if (has_bias && col < p.L) v = fmaf(__ldg(brow + n * 8 + e), LOG2E, v);
+          v = col < p.L ? v : -INFINITY;
+          s[n][2 * r + e] = v;
+          mx = fmaxf(mx, v);
+        }
       }
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -164,7 +202,7 @@ __device__ __forceinline__ void softmax_dropout(float (&s)[LP / 8][4], uint32_t 
     for (int n = 0; n < LP / 8; ++n) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float pr = exp2f((s[n][2 * r + e] - mx) * LOG2E);
+        const float pr = ex2_approx(s[n][2 * r + e] - mx);
         s[n][2 * r + e] = pr;
         sum += pr;
       }
@@ -215,88 +253,108 @@ struct Ring {
   static constexpr int NC = DK / 64;
   static constexpr int CT = LP * 128;
   static constexpr int STAGE = 2 * CT;
-  static constexpr int SPW = (BWD ? 4 : 2) * NC;  // stages per window
+  static constexpr int NPH = BWD ? 4 : 2;  // phases per window, NC stages each
 
   const Params& p;
   uint32_t base;
-  int h;
-  int64_t n_it;     // windows this CTA processes
-  // producer cursor (next stage to issue) and consumer slot, all maintained incrementally (no div / mod)
-  int64_t w_p;      // window of the next stage to issue
-  int ph_p, c_p;    // its phase / chunk
-  int slot_p, slot_c;
+  int n_it;  // windows this CTA processes
+  TileCopy<LP> cp;
+  // producer cursor (next stage to issue) and consumer slot, all maintained incrementally (no div / mod / 64-bit
+  // multiplies in the loop): gq / gd point at this thread's first piece of chunk 0 of Q / dO of window w_p
+  int w_p, ph_p, c_p;
+  uint32_t off_p, off_c;  // byte offsets of the producer / consumer stage
+  const __nv_bfloat16 *gq, *gd;
+  int64_t wstep_q, wstep_d, kstep_q, kstep_d;
+  int HD;
 
-  __device__ Ring(const Params& p_, uint32_t base_, int h_) : p(p_), base(base_), h(h_) {
-    n_it = (p.W - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
-    if (n_it < 0) n_it = 0;
+  __device__ Ring(const Params& p_, uint32_t base_, int h) : p(p_), base(base_) {
+    const int W = (int)p.W;
+    n_it = ((int)blockIdx.x < W) ? (W - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    cp.init(p.L);
     w_p = blockIdx.x;
-    ph_p = 0; c_p = 0; slot_p = 0; slot_c = NS - 1;  // slot_c is advanced to 0 by the first acquire()
+    ph_p = 0; c_p = 0;
+    off_p = 0; off_c = (NS - 1) * STAGE;  // off_c is advanced to 0 by the first acquire()
+    HD = p.H * DK;
+    const int r0 = threadIdx.x >> 3, c16 = threadIdx.x & 7;
+    gq = p.qkv + ((int64_t)w_p * p.L + r0) * p.ld + h * DK + c16 * 8;
+    wstep_q = (int64_t)gridDim.x * p.L * p.ld;
+    kstep_q = (int64_t)TileCopy<LP>::RSTEP * p.ld;
+    gd = nullptr; wstep_d = 0; kstep_d = 0;
+    if (BWD) {
+      gd = p.dout + ((int64_t)w_p * p.L + r0) * p.ld_dout + h * DK + c16 * 8;
+      wstep_d = (int64_t)gridDim.x * p.L * p.ld_dout;
+      kstep_d = (int64_t)TileCopy<LP>::RSTEP * p.ld_dout;
+    }
   }
-  __device__ uint32_t cur(int which) const { return base + (uint32_t)slot_c * STAGE + which * CT; }
+  __device__ __forceinline__ uint32_t cur(int which) const { return base + off_c + which * CT; }
 
-  __device__ void issue_next() {
-    if (w_p < p.W) {
-      const int HD = p.H * DK;
-      const __nv_bfloat16* q = p.qkv + (w_p * p.L) * p.ld + h * DK + c_p * 64;
-      const uint32_t t0 = base + (uint32_t)slot_p * STAGE, t1 = t0 + CT;
+  __device__ __forceinline__ void issue_next() {
+    if (w_p < (int)p.W) {
+      const __nv_bfloat16* q = gq + c_p * 64;
+      const uint32_t t0 = base + off_p, t1 = t0 + CT;
       if (!BWD) {
         if (ph_p == 0) {
-          load_chunk_tile<LP>(t0, q, p.ld, p.L);
-          load_chunk_tile<LP>(t1, q + HD, p.ld, p.L);
+          cp.load(t0, q, kstep_q, p.qkv);
+          cp.load(t1, q + HD, kstep_q, p.qkv);
         } else {
-          load_chunk_tile<LP>(t0, q + 2 * HD, p.ld, p.L);
+          cp.load(t0, q + 2 * HD, kstep_q, p.qkv);
         }
       } else {
-        const __nv_bfloat16* d_o = p.dout + (w_p * p.L) * p.ld_dout + h * DK + c_p * 64;
+        const __nv_bfloat16* d_o = gd + c_p * 64;
         if (ph_p == 0) {
-          load_chunk_tile<LP>(t0, q, p.ld, p.L);
-          load_chunk_tile<LP>(t1, q + HD, p.ld, p.L);
+          cp.load(t0, q, kstep_q, p.qkv);
+          cp.load(t1, q + HD, kstep_q, p.qkv);
         } else if (ph_p == 1) {
-          load_chunk_tile<LP>(t0, d_o, p.ld_dout, p.L);
-          load_chunk_tile<LP>(t1, q + 2 * HD, p.ld, p.L);
+          cp.load(t0, d_o, kstep_d, p.qkv);
+          cp.load(t1, q + 2 * HD, kstep_q, p.qkv);
         } else if (ph_p == 2) {
-          load_chunk_tile<LP>(t0, q + HD, p.ld, p.L);  // K_c
-          load_chunk_tile<LP>(t1, q, p.ld, p.L);       // Q_c
+          cp.load(t0, q + HD, kstep_q, p.qkv);  // K_c
+          cp.load(t1, q, kstep_q, p.qkv);       // Q_c
         } else {
-          load_chunk_tile<LP>(t0, d_o, p.ld_dout, p.L);
+          cp.load(t0, d_o, kstep_d, p.qkv);
         }
       }
       if (++c_p == NC) {
         c_p = 0;
-        if (++ph_p == (BWD ? 4 : 2)) {
+        if (++ph_p == NPH) {
           ph_p = 0;
           w_p += gridDim.x;
+          gq += wstep_q;
+          if (BWD) gd += wstep_d;
         }
       }
-      slot_p = (slot_p + 1 == NS) ? 0 : slot_p + 1;
+      off_p = (off_p + STAGE == NS * STAGE) ? 0u : off_p + STAGE;
     }
     cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
   }
-  __device__ void prologue() {
+  __device__ __forceinline__ void prologue() {
 #pragma unroll
     for (int i = 0; i < NS - 1; ++i) issue_next();
   }
   // Makes the next stage resident and visible to all warps (-> cur()), then refills the slot consumed one step earlier.
-  __device__ void acquire() {
+  __device__ __forceinline__ void acquire() {
     cp_async_wait<NS - 2>();
     __syncthreads();
-    slot_c = (slot_c + 1 == NS) ? 0 : slot_c + 1;
+    off_c = (off_c + STAGE == NS * STAGE) ? 0u : off_c + STAGE;
     issue_next();
   }
 };
 
 // writes a finished 16x64 fp32 fragment block (rows row0.., 64 columns at gbase) as bf16: each quad stores 16
 // contiguous bytes per row and n-tile; L2 merges the two halves of a 32-byte sector before it reaches HBM
-__device__ __forceinline__ void store_chunk(const float (&acc)[8][4], float mul, __nv_bfloat16* gbase, int64_t ld_out,
-                                            int row0, int L, int lane) {
+__device__ __forceinline__ void store_chunk(const float (&acc)[8][4], __nv_bfloat16* gbase, int64_t ld_out, int row0,
+                                            int L, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  const int r0 = row0 + g, r1 = row0 + g + 8;
+  const int r0 = row0 + g;
+  uint32_t* p0 = reinterpret_cast<uint32_t*>(gbase + (int64_t)r0 * ld_out + 2 * t);
+  uint32_t* p1 = reinterpret_cast<uint32_t*>(gbase + (int64_t)(r0 + 8) * ld_out + 2 * t);
+  if (r0 < L) {
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    if (r0 < L)
-      *reinterpret_cast<uint32_t*>(gbase + (int64_t)r0 * ld_out + n * 8 + 2 * t) = pack_bf16x2(acc[n][0] * mul, acc[n][1] * mul);
-    if (r1 < L)
-      *reinterpret_cast<uint32_t*>(gbase + (int64_t)r1 * ld_out + n * 8 + 2 * t) = pack_bf16x2(acc[n][2] * mul, acc[n][3] * mul);
+    for (int n = 0; n < 8; ++n) p0[n * 4] = pack_bf16x2(acc[n][0], acc[n][1]);
+  }
+  if (r0 + 8 < L) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) p1[n * 4] = pack_bf16x2(acc[n][2], acc[n][3]);
   }
 }
 
@@ -317,8 +375,8 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p_i
   const int m0 = warp * 16;
   R ring(p, s0, h);
   ring.prologue();
-  for (int64_t it = 0; it < ring.n_it; ++it) {
-    const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
+  for (int it = 0; it < ring.n_it; ++it) {
+    const int64_t w = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
     float s[NT][4];
     uint32_t keep[2];
 #pragma unroll
@@ -361,7 +419,7 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p_i
       ring.acquire();
       float o[8][4];
       mma_frag_x_rows<KT>(o, pa, ring.cur(0), lane);
-      store_chunk(o, 1.0f, obase + c * 64, p.ld_out, m0, p.L, lane);
+      store_chunk(o, obase + c * 64, p.ld_out, m0, p.L, lane);
     }
   }
   cp_async_wait<0>();
@@ -394,8 +452,8 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
   }
   R ring(p, s0, h);
   ring.prologue();
-  for (int64_t it = 0; it < ring.n_it; ++it) {
-    const int64_t w = (int64_t)blockIdx.x + it * gridDim.x;
+  for (int it = 0; it < ring.n_it; ++it) {
+    const int64_t w = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
     {
       // ---- phase A: S = Q K^T, dP = dO V^T for this warp's query rows ----
       float s[NT][4], dp[NT][4];
@@ -453,8 +511,9 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
                                                             dropped(s[n][1], keep, n, 1, p.drop_scale)));
         st_shared_b32(sPd + (m0 + g + 8) * PP + cb, pack_bf16x2(dropped(s[n][2], keep, n, 2, p.drop_scale),
                                                                 dropped(s[n][3], keep, n, 3, p.drop_scale)));
-        st_shared_b32(sDS + (m0 + g) * PP + cb, pack_bf16x2(dp[n][0], dp[n][1]));
-        st_shared_b32(sDS + (m0 + g + 8) * PP + cb, pack_bf16x2(dp[n][2], dp[n][3]));
+        // the 1/sqrt(dk) of dQ = scale * dS K and dK = scale * dS^T Q is folded into the bf16 copy of dS
+        st_shared_b32(sDS + (m0 + g) * PP + cb, pack_bf16x2(dp[n][0] * p.scale, dp[n][1] * p.scale));
+        st_shared_b32(sDS + (m0 + g + 8) * PP + cb, pack_bf16x2(dp[n][2] * p.scale, dp[n][3] * p.scale));
       }
     }
     // ---- phase B ----
@@ -476,10 +535,10 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
           }
         }
         float acc[8][4];
-        mma_frag_x_rows<KT>(acc, a_ds, ring.cur(0), lane);   // dQ_c = scale * dS K_c
-        store_chunk(acc, p.scale, dq_base + c * 64, p.ld_out, m0, p.L, lane);
-        mma_frag_x_rows<KT>(acc, a_dst, ring.cur(1), lane);  // dK_c = scale * dS^T Q_c
-        store_chunk(acc, p.scale, dk_base + c * 64, p.ld_out, m0, p.L, lane);
+        mma_frag_x_rows<KT>(acc, a_ds, ring.cur(0), lane);   // dQ_c = (scale dS) K_c
+        store_chunk(acc, dq_base + c * 64, p.ld_out, m0, p.L, lane);
+        mma_frag_x_rows<KT>(acc, a_dst, ring.cur(1), lane);  // dK_c = (scale dS)^T Q_c
+        store_chunk(acc, dk_base + c * 64, p.ld_out, m0, p.L, lane);
       }
     }
     {
@@ -492,7 +551,7 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kerne
         ring.acquire();
         float acc[8][4];
         mma_frag_x_rows<KT>(acc, a_pdt, ring.cur(0), lane);  // dV_c = Pd^T dO_c
-        store_chunk(acc, 1.0f, dv_base + c * 64, p.ld_out, m0, p.L, lane);
+        store_chunk(acc, dv_base + c * 64, p.ld_out, m0, p.L, lane);
       }
     }
   }
@@ -588,7 +647,8 @@ extern "C" int lstc_attn_fwd(const void* qkv, int64_t ld, int64_t W, int L, int 
                              float scale, float dropout_p, uint64_t seed, uint64_t offset, void* out,
                              int64_t ld_out, float* probs, void* stream) {
   LSTC_CHECK_ARG(qkv && out, "lstc_attn_fwd: null pointer");
-  LSTC_CHECK_ARG(W >= 0 && L >= 1 && H >= 1, "lstc_attn_fwd: bad sizes W=%lld L=%d H=%d", (long long)W, L, H);
+  LSTC_CHECK_ARG(W >= 0 && W < (int64_t)2000000000 && L >= 1 && H >= 1, "lstc_attn_fwd: bad sizes W=%lld L=%d H=%d",
+                 (long long)W, L, H);
   LSTC_CHECK_ARG(ld % 8 == 0 && ld_out % 8 == 0 && ld >= 3 * (int64_t)H * dk && ld_out >= (int64_t)H * dk,
                  "lstc_attn_fwd: leading dims must be multiples of 8 and cover all heads");
   LSTC_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "lstc_attn_fwd: 16-byte alignment");
@@ -606,7 +666,7 @@ extern "C" int lstc_attn_bwd(const void* qkv, int64_t ld, const void* dout, int6
                              int H, int dk, const float* bias, float scale, float dropout_p, uint64_t seed,
                              uint64_t offset, void* dqkv, int64_t ld_dqkv, float* dbias, void* stream) {
   LSTC_CHECK_ARG(qkv && dout && dqkv, "lstc_attn_bwd: null pointer");
-  LSTC_CHECK_ARG(W >= 0 && L >= 1 && H >= 1, "lstc_attn_bwd: bad sizes");
+  LSTC_CHECK_ARG(W >= 0 && W < (int64_t)2000000000 && L >= 1 && H >= 1, "lstc_attn_bwd: bad sizes");
   LSTC_CHECK_ARG(ld % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0 && ld >= 3 * (int64_t)H * dk &&
                      ld_dqkv >= 3 * (int64_t)H * dk && ld_dout >= (int64_t)H * dk,
                  "lstc_attn_bwd: leading dims must be multiples of 8 and cover all heads");

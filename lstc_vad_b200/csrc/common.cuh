@@ -85,8 +85,11 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------
-// Counter-based dropout RNG: Philox4x32-10.  One call yields 128 random bits =
-// eight 16-bit lanes, i.e. the keep/drop decision for 8 consecutive elements.
+// Counter-based dropout RNG: Philox4x32 with 7 rounds (the shortest variant that is
+// Crush-resistant in Salmon et al., SC'11; dropout masks need no larger margin and
+// the rounds are pure ALU work inside bandwidth- and issue-bound kernels).  One call
+// yields 128 random bits = eight 16-bit lanes, i.e. the keep/drop decision for 8
+// consecutive elements.
 // The mask of element (row, col) of a [rows, ld8*8] grid depends only on
 // (seed, offset, row*ld8 + col/8) so forward and backward kernels regenerate
 // the same mask without storing it (reference keeps masks inside autograd:
@@ -101,16 +104,42 @@ __host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 
-__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t offset, uint64_t idx,
-                                                       uint32_t (&out)[4]) {
+constexpr int PHILOX_ROUNDS = 7;
+__host__ __device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t offset, uint64_t idx,
+                                                    uint32_t (&out)[4]) {
   uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     philox_round(c, k0, k1);
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// Same generator with the round keys expanded once (they depend on the seed only): kernels that draw many masks keep
+// the 2*PHILOX_ROUNDS keys in (uniform) registers instead of re-deriving them per call.
+struct PhiloxKeys {
+  uint32_t k0[PHILOX_ROUNDS], k1[PHILOX_ROUNDS];
+};
+__host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
+    k.k0[r] = a;
+    k.k1[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return k;
+}
+__host__ __device__ __forceinline__ void philox4x32_keyed(const PhiloxKeys& k, uint64_t offset, uint64_t idx,
+                                                          uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+#pragma unroll
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) philox_round(c, k.k0[r], k.k1[r]);
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
@@ -122,11 +151,20 @@ __host__ __device__ __forceinline__ uint32_t dropout_threshold16(float p) {
   return (uint32_t)t;
 }
 
+// raw form of dropout_keep8 for kernels that select per element: element 8*idx8 + j is KEPT when
+// dropout_kept(r, j, thr16), with r the four words this returns
+__host__ __device__ __forceinline__ void dropout_rand8(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t (&r)[4]) {
+  philox4x32(seed, offset, idx8, r);
+}
+__host__ __device__ __forceinline__ bool dropout_kept(const uint32_t (&r)[4], int j, uint32_t thr16) {
+  return ((j & 1) ? (r[j >> 1] >> 16) : (r[j >> 1] & 0xffffu)) >= thr16;
+}
+
 // 8-bit keep mask (bit j set => element 8*idx8 + j is kept)
 __host__ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t idx8,
                                                            uint32_t thr16) {
   uint32_t r[4];
-  philox4x32_10(seed, offset, idx8, r);
+  philox4x32(seed, offset, idx8, r);
   uint32_t m = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {

@@ -2,11 +2,14 @@
 // Replaces nn.LayerNorm(d_model, eps=1e-6) at models/Encoder.py:31,48-49,
 // models/MultiHeadAttention.py:47,125-126 and models/FFN.py:10,20-21 (and its autograd backward).
 //
-// One CTA walks over rows (grid-stride); thread t owns the same 8*NV columns of every row, so
+// One CTA walks over groups of RPI rows (grid-stride); thread t owns the same 8*NV columns of every row, so
 //   - each row is one fully coalesced 16-byte-per-thread read and write,
-//   - the per-column dgamma / dbeta sums of the backward stay in registers for the whole kernel and
-//     are flushed once per CTA into a partial buffer that a second tiny kernel reduces
+//   - gamma / beta (forward) and the per-column dgamma / dbeta / dx sums (backward) stay in registers for the whole
+//     kernel; the backward flushes them once per CTA into a partial buffer that a second tiny kernel reduces
 //     (deterministic, no atomics).
+// Both kernels are bound by HBM only if they stay lean: the row statistics of RPI rows are reduced TOGETHER
+// (halving butterfly in the warp, one barrier, a 32-lane second stage), which costs ~1.7 instructions per element
+// instead of the ~10 of per-row shuffle trees plus an all-warps smem read.
 #include "common.cuh"
 #include "../../include/lstc_vad_b200.h"
 
@@ -28,44 +31,56 @@ __device__ __forceinline__ void load8(const void* base, int64_t off, float (&f)[
 }
 // streaming (evict-first) stores: the row is not re-read by this kernel and is larger than what L2 can keep for the
 // consumer anyway; keeping it from displacing the rows still to be read helps the read stream
-template <bool IS_F32>
-__device__ __forceinline__ void store8(void* base, int64_t off, const float (&f)[8]) {
-  if (IS_F32) {
-    float* p = reinterpret_cast<float*>(base) + off;
-    __stcs(reinterpret_cast<float4*>(p), make_float4(f[0], f[1], f[2], f[3]));
-    __stcs(reinterpret_cast<float4*>(p + 4), make_float4(f[4], f[5], f[6], f[7]));
-  } else {
-    __stcs(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off), pack8(f));
-  }
+__device__ __forceinline__ void store8_f32(float* p, const float (&f)[8]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(f[0], f[1], f[2], f[3]));
+  __stcs(reinterpret_cast<float4*>(p + 4), make_float4(f[4], f[5], f[6], f[7]));
 }
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const uint4& v) { __stcs(reinterpret_cast<uint4*>(p), v); }
 
-// block-wide sums of N values at once; `buf` is a [2][MAX_WARPS][N] smem scratch, `phase` alternates per call so a
-// single barrier per reduction suffices
+// CTA-wide sums of N values per thread (N = 2, 4 or 8; one value per row statistic).  `scratch` is
+// [2][MAX_WARPS][N] floats, zero-initialised once (warps that do not exist contribute zeros); `phase` alternates so
+// that one barrier per call suffices.
+//   stage 1: halving butterfly -- at each step a lane keeps half of its values and hands the other half to its
+//            partner, so N values cost N-1 + (5 - log2 N) shuffles instead of 5 N; lane l ends with the warp total
+//            of value l >> (5 - log2 N);
+//   stage 2: after the barrier lane l fetches the partial of warp (l & 7) for value (l >> 3) [+4], three xor
+//            steps add the 8 warps, and N broadcasts hand every total to every lane.
 template <int N>
-__device__ __forceinline__ void block_sum_n(float (&v)[N], float (*buf)[MAX_WARPS][N], int& phase) {
+__device__ __forceinline__ void block_sum(float (&v)[N], float* scratch, int& phase, int lane, int warp) {
+  static_assert(N == 2 || N == 4 || N == 8, "block_sum: N must be 2, 4 or 8");
+  constexpr int LG = (N == 8) ? 3 : (N == 4) ? 2 : 1;
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  if (lane == 0) {
+  for (int s = 0; s < LG; ++s) {
+    const int n = N >> s, mask = 16 >> s;
+    const bool up = (lane & mask) != 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) buf[phase][warp][i] = v[i];
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
   }
+#pragma unroll
+  for (int s = LG; s < 5; ++s) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16 >> s);
+  float* S = scratch + phase * (MAX_WARPS * N);
+  if ((lane & ((32 >> LG) - 1)) == 0) S[warp * N + (lane >> (5 - LG))] = v[0];
   __syncthreads();
+  float a = S[(lane & 7) * N + ((lane >> 3) & (N - 1))];
+  float b = 0.f;
+  if (N == 8) b = S[(lane & 7) * N + (lane >> 3) + 4];
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = 0.f;
-  for (int w = 0; w < nw; ++w) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] += buf[phase][w][i];
+  for (int o = 1; o < 8; o <<= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (N == 8) b += __shfl_xor_sync(0xffffffffu, b, o);
   }
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __shfl_sync(0xffffffffu, (i < 4) ? a : b, (i & 3) * 8);
   phase ^= 1;
 }
 
-constexpr int RPI = 2;   // forward: rows per CTA iteration (half the barriers per row)
-constexpr int NSTG = 4;  // depth of the per-thread cp.async row ring
-
 // Every thread stages ITS OWN 16/32-byte chunks of the next NSTG-1 iterations in shared memory with cp.async and is
 // the only reader of those bytes, so the ring needs no barrier: cp.async.wait_group on the thread's own groups is
-// enough.  This keeps ~3 rows per CTA in flight without holding them in registers.
+// enough.  This keeps ~3 iterations per CTA in flight without holding them in registers.
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -74,15 +89,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-template <bool IS_F32>
-__device__ __forceinline__ void stage8(uint32_t dst, const void* base, int64_t off) {
-  if (IS_F32) {
-    cp_async16(dst, reinterpret_cast<const float*>(base) + off);
-    cp_async16(dst + 16, reinterpret_cast<const float*>(base) + off + 4);
-  } else {
-    cp_async16(dst, reinterpret_cast<const __nv_bfloat16*>(base) + off);
-  }
 }
 template <bool IS_F32>
 __device__ __forceinline__ void unstage8(uint32_t src, float (&f)[8]) {
@@ -98,148 +104,210 @@ __device__ __forceinline__ void unstage8(uint32_t src, float (&f)[8]) {
   }
 }
 
-template <int NV, bool X_F32, bool Y_F32>
+template <bool IS_F32>
+__device__ __forceinline__ void stage8b(uint32_t dst, const char* src) {
+  cp_async16(dst, src);
+  if (IS_F32) cp_async16(dst + 16, src + 16);
+}
+__device__ __forceinline__ float rsqrt_approx(float v) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
+
+// Forward: two passes over the registers (mean, then the sum of squared deviations -- the same order of operations
+// as the reference's nn.LayerNorm, no E[x^2] - mean^2 cancellation), two block_sum calls per RPI rows.  Global
+// pointers, ring offsets and the group counter advance incrementally; only the ragged last group takes the
+// row-predicated store path.
+template <int NV, int RPI, int NSTG, bool X_F32, bool Y_F32>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, void* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                     int64_t rows, int D, float eps) {
-  __shared__ float buf[2][MAX_WARPS][RPI];
+                                                     int rows, int D, float eps) {
+  __shared__ float scratch[2 * MAX_WARPS * RPI];
   extern __shared__ __align__(16) uint8_t ring_raw[];
-  constexpr int XB = X_F32 ? 32 : 16;
+  constexpr int XB = X_F32 ? 32 : 16, XE = X_F32 ? 4 : 2, YE = Y_F32 ? 4 : 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  for (int i = tid; i < 2 * MAX_WARPS * RPI; i += nthr) scratch[i] = 0.f;
+  __syncthreads();
   int phase = 0;
-  const int tid = threadIdx.x;
-  const uint32_t ring = smem_addr(ring_raw);
-  const uint32_t stage_bytes = RPI * NV * blockDim.x * XB;
-  auto slot = [&](int st, int r, int v) { return ring + st * stage_bytes + ((r * NV + v) * blockDim.x + tid) * XB; };
-  auto issue = [&](int64_t row0, int st) {
-    if (row0 < rows) {
+  bool act[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) act[v] = (v * nthr + tid) * 8 < D;
+  const int vcols = nthr * 8;  // column distance between the chunks of one thread
+  const uint32_t chunk_stride = nthr * XB, stage_bytes = RPI * NV * chunk_stride, ring_bytes = NSTG * stage_bytes;
+  const uint32_t ring = smem_addr(ring_raw) + tid * XB;
+  const int ngroups = (rows + RPI - 1) / RPI;
+  const int64_t first = ((int64_t)blockIdx.x * RPI) * D + tid * 8;  // element offset of this thread's first chunk
+  const char* xg = reinterpret_cast<const char*>(x) + first * XE;
+  const int64_t xg_step = (int64_t)gridDim.x * RPI * D * XE;
+  int g_issue = blockIdx.x;
+  uint32_t st_issue = 0;
+  auto issue = [&]() {
+    if (g_issue < ngroups) {
+      const int nvalid = rows - g_issue * RPI;
 #pragma unroll
       for (int r = 0; r < RPI; ++r) {
-        if (row0 + r < rows) {
+        if (r < nvalid) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            const int c = (v * blockDim.x + tid) * 8;
-            if (c < D) stage8<X_F32>(slot(st, r, v), x, (row0 + r) * D + c);
-          }
+          for (int v = 0; v < NV; ++v)
+            if (act[v])
+              stage8b<X_F32>(ring + st_issue + (r * NV + v) * chunk_stride, xg + ((int64_t)r * D + v * vcols) * XE);
         }
       }
+      xg += xg_step;
     }
+    g_issue += gridDim.x;
+    st_issue = (st_issue + stage_bytes == ring_bytes) ? 0u : st_issue + stage_bytes;
     cp_async_commit();
   };
   float gm[NV][8], bt[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const int c = (v * blockDim.x + tid) * 8;
-    if (c < D) {
-      load8<true>(gamma, c, gm[v]);
-      load8<true>(beta, c, bt[v]);
+    if (act[v]) {
+      load8<true>(gamma, (v * nthr + tid) * 8, gm[v]);
+      load8<true>(beta, (v * nthr + tid) * 8, bt[v]);
     }
   }
   const float invD = 1.0f / (float)D;
-  const int64_t step = (int64_t)gridDim.x * RPI;
 #pragma unroll
-  for (int i = 0; i < NSTG - 1; ++i) issue((int64_t)blockIdx.x * RPI + i * step, i);
-  int st = 0;
-  for (int64_t row0 = (int64_t)blockIdx.x * RPI; row0 < rows; row0 += step) {
+  for (int i = 0; i < NSTG - 1; ++i) issue();
+  uint32_t st_read = 0;
+  char* yg = reinterpret_cast<char*>(y) + first * YE;
+  const int64_t yg_step = (int64_t)gridDim.x * RPI * D * YE;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
     cp_async_wait<NSTG - 2>();
     float xv[RPI][NV][8];
     float s[RPI];
 #pragma unroll
     for (int r = 0; r < RPI; ++r) {
       s[r] = 0.f;
-      if (row0 + r < rows) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = (v * blockDim.x + tid) * 8;
-          if (c < D) {
-            unstage8<X_F32>(slot(st, r, v), xv[r][v]);
+      for (int v = 0; v < NV; ++v) {
+        if (act[v]) {
+          unstage8<X_F32>(ring + st_read + (r * NV + v) * chunk_stride, xv[r][v]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s[r] += xv[r][v][j];
+          for (int j = 0; j < 8; ++j) s[r] += xv[r][v][j];
+        }
+      }
+    }
+    st_read = (st_read + stage_bytes == ring_bytes) ? 0u : st_read + stage_bytes;
+    issue();  // refills the slot consumed one iteration ago
+    block_sum<RPI>(s, scratch, phase, lane, warp);
+    float q[RPI];
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      s[r] *= invD;  // mean
+      q[r] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (act[v]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xv[r][v][j] -= s[r];
+            q[r] = fmaf(xv[r][v][j], xv[r][v][j], q[r]);
           }
         }
       }
     }
-    issue(row0 + (NSTG - 1) * step, st == 0 ? NSTG - 1 : st - 1);  // refills the slot consumed one iteration ago
-    st = (st + 1 == NSTG) ? 0 : st + 1;
-    block_sum_n<RPI>(s, buf, phase);
-    float mean[RPI], q[RPI];
+    block_sum<RPI>(q, scratch, phase, lane, warp);
 #pragma unroll
-    for (int r = 0; r < RPI; ++r) {
-      mean[r] = s[r] * invD;
-      q[r] = 0.f;
-      if (row0 + r < rows) {
+    for (int r = 0; r < RPI; ++r) q[r] = rsqrt_approx(fmaf(q[r], invD, eps));  // rstd
+    const int nvalid = rows - g * RPI;
+    auto emit = [&](auto full) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = (v * blockDim.x + tid) * 8;
-          if (c < D) {
+      for (int r = 0; r < RPI; ++r) {
+        if (decltype(full)::value || r < nvalid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float d = xv[r][v][j] - mean[r];
-              q[r] += d * d;
+          for (int v = 0; v < NV; ++v) {
+            if (act[v]) {
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = fmaf(xv[r][v][j] * q[r], gm[v][j], bt[v][j]);
+              char* dst = yg + ((int64_t)r * D + v * vcols) * YE;
+              if (Y_F32) store8_f32(reinterpret_cast<float*>(dst), o);
+              else store8_bf16(reinterpret_cast<__nv_bfloat16*>(dst), pack8(o));
             }
           }
-        }
-      }
-    }
-    block_sum_n<RPI>(q, buf, phase);
-#pragma unroll
-    for (int r = 0; r < RPI; ++r) {
-      if (row0 + r < rows) {
-        const float rstd = rsqrtf(q[r] * invD + eps);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = (v * blockDim.x + tid) * 8;
-          if (c < D) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (xv[r][v][j] - mean[r]) * rstd * gm[v][j] + bt[v][j];
-            store8<Y_F32>(y, (row0 + r) * D + c, o);
+          if (tid == 0) {
+            mean_out[(int64_t)g * RPI + r] = s[r];
+            rstd_out[(int64_t)g * RPI + r] = q[r];
           }
         }
-        if (tid == 0) {
-          mean_out[row0 + r] = mean[r];
-          rstd_out[row0 + r] = rstd;
-        }
       }
-    }
+    };
+    if (nvalid >= RPI) emit(BoolTag<true>());
+    else emit(BoolTag<false>());
+    yg += yg_step;
   }
   cp_async_wait<0>();
 }
 
-template <int NV, bool DY_F32, bool X_F32, bool DX_F32>
-__global__ void __launch_bounds__(256)
+// Backward: dx = rstd * (dy*gamma - mean_D(dy*gamma) - xhat * mean_D(dy*gamma*xhat)); one block_sum of 2*RPI values
+// per RPI rows.  Optionally also writes dropout(dx) (the gradient entering the sub-layer whose output was dropped
+// before the residual add) and accumulates the column sums of the tensor the preceding Linear receives.
+template <int NV, int RPI, int NSTG, bool DY_F32, bool X_F32, bool DX_F32>
+__global__ void __launch_bounds__(256, (NV == 1 && !X_F32) ? 2 : 1)
 ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, void* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_drop, float drop_scale, uint32_t drop_thr16, uint64_t seed,
-              uint64_t offset, float* __restrict__ partial /*[grid][3][D]*/, int want_dxsum, int64_t rows, int D) {
+              uint64_t offset, float* __restrict__ partial /*[grid][3][D]*/, int want_dxsum, int rows, int D) {
   offset += rng_step();
-  __shared__ float buf[2][MAX_WARPS][2];
+  __shared__ float scratch[2 * MAX_WARPS * 2 * RPI];
   extern __shared__ __align__(16) uint8_t ring_raw[];
   constexpr int XB = X_F32 ? 32 : 16, YB = DY_F32 ? 32 : 16;
+  constexpr int XE = X_F32 ? 4 : 2, YE = DY_F32 ? 4 : 2, OE = DX_F32 ? 4 : 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  for (int i = tid; i < 2 * MAX_WARPS * 2 * RPI; i += nthr) scratch[i] = 0.f;
+  __syncthreads();
   int phase = 0;
-  const int tid = threadIdx.x;
-  const uint32_t ring = smem_addr(ring_raw);
-  const uint32_t stage_bytes = NV * blockDim.x * (XB + YB);
-  auto x_slot = [&](int st, int v) { return ring + st * stage_bytes + (v * blockDim.x + tid) * XB; };
-  auto dy_slot = [&](int st, int v) { return ring + st * stage_bytes + NV * blockDim.x * XB + (v * blockDim.x + tid) * YB; };
-  auto issue = [&](int64_t row, int st) {
-    if (row < rows) {
+  bool act[NV];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = (v * blockDim.x + tid) * 8;
-        if (c < D) {
-          stage8<X_F32>(x_slot(st, v), x, row * D + c);
-          stage8<DY_F32>(dy_slot(st, v), dy, row * D + c);
+  for (int v = 0; v < NV; ++v) act[v] = (v * nthr + tid) * 8 < D;
+  const int vcols = nthr * 8;
+  // stage layout: [RPI][NV] x chunks, then [RPI][NV] dy chunks
+  const uint32_t xstride = nthr * XB, ystride = nthr * YB;
+  const uint32_t stage_bytes = RPI * NV * (xstride + ystride), ring_bytes = NSTG * stage_bytes;
+  const uint32_t xring = smem_addr(ring_raw) + tid * XB;
+  const uint32_t yring = smem_addr(ring_raw) + RPI * NV * xstride + tid * YB;
+  const int ngroups = (rows + RPI - 1) / RPI;
+  const int64_t first = ((int64_t)blockIdx.x * RPI) * D + tid * 8;
+  const int64_t gstep = (int64_t)gridDim.x * RPI * D;  // elements between consecutive groups of this CTA
+  const char* xg = reinterpret_cast<const char*>(x) + first * XE;
+  const char* yg = reinterpret_cast<const char*>(dy) + first * YE;
+  int g_issue = blockIdx.x;
+  uint32_t st_issue = 0;
+  auto issue = [&]() {
+    if (g_issue < ngroups) {
+      const int nvalid = rows - g_issue * RPI;
+#pragma unroll
+      for (int r = 0; r < RPI; ++r) {
+        if (r < nvalid) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if (act[v]) {
+              const int64_t e = (int64_t)r * D + v * vcols;
+              stage8b<X_F32>(xring + st_issue + (r * NV + v) * xstride, xg + e * XE);
+              stage8b<DY_F32>(yring + st_issue + (r * NV + v) * ystride, yg + e * YE);
+            }
+          }
         }
       }
+      xg += gstep * XE;
+      yg += gstep * YE;
     }
+    g_issue += gridDim.x;
+    st_issue = (st_issue + stage_bytes == ring_bytes) ? 0u : st_issue + stage_bytes;
     cp_async_commit();
   };
   float gm[NV][8], dg[NV][8], db[NV][8], dxs[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const int c = (v * blockDim.x + tid) * 8;
-    if (c < D) load8<true>(gamma, c, gm[v]);
+    if (act[v]) load8<true>(gamma, (v * nthr + tid) * 8, gm[v]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       dg[v][j] = 0.f;
@@ -248,89 +316,139 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const flo
     }
   }
   const float invD = 1.0f / (float)D;
-  const int64_t ld8 = D >> 3;
+  const PhiloxKeys keys = philox_keys(seed);
+  const int ld8 = D >> 3;
+  uint64_t idx8 = (uint64_t)blockIdx.x * RPI * ld8 + tid;  // dropout counter of this thread's first chunk
+  const uint64_t idx8_step = (uint64_t)gridDim.x * RPI * ld8;
 #pragma unroll
-  for (int i = 0; i < NSTG - 1; ++i) issue((int64_t)blockIdx.x + (int64_t)i * gridDim.x, i);
-  int st = 0;
-  int64_t row = blockIdx.x;
-  float nmean = 0.f, nrstd = 0.f;
-  if (row < rows) {
-    nmean = __ldg(mean_in + row);
-    nrstd = __ldg(rstd_in + row);
-  }
-  for (; row < rows; row += gridDim.x) {
+  for (int i = 0; i < NSTG - 1; ++i) issue();
+  uint32_t st_read = 0;
+  char* og = reinterpret_cast<char*>(dx) + first * OE;
+  __nv_bfloat16* odg = dx_drop != nullptr ? dx_drop + first : nullptr;
+  float nrs[RPI], nnb[RPI];  // next group's rstd and -mean*rstd (0 for rows past the end)
+  auto fetch_stats = [&](int g) {
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      nrs[r] = 0.f;
+      nnb[r] = 0.f;
+      if (g < ngroups && g * RPI + r < rows) {
+        nrs[r] = __ldg(rstd_in + (int64_t)g * RPI + r);
+        nnb[r] = -__ldg(mean_in + (int64_t)g * RPI + r) * nrs[r];
+      }
+    }
+  };
+  fetch_stats(blockIdx.x);
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
     cp_async_wait<NSTG - 2>();
-    float xh[NV][8], dyg[NV][8];
-    const float mean = nmean, rstd = nrstd;
+    float xh[RPI][NV][8], dgm[RPI][NV][8];
+    float rs[RPI], nb[RPI];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-        unstage8<X_F32>(x_slot(st, v), xh[v]);
-        unstage8<DY_F32>(dy_slot(st, v), dyg[v]);
-      }
-    }
-    issue(row + (int64_t)(NSTG - 1) * gridDim.x, st == 0 ? NSTG - 1 : st - 1);  // slot consumed one iteration ago
-    st = (st + 1 == NSTG) ? 0 : st + 1;
-    const int64_t nrow = row + gridDim.x;
-    if (nrow < rows) {
-      nmean = __ldg(mean_in + nrow);
-      nrstd = __ldg(rstd_in + nrow);
-    }
-    float red[2] = {0.f, 0.f};
+    for (int r = 0; r < RPI; ++r) {
+      rs[r] = nrs[r];
+      nb[r] = nnb[r];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xhat = (xh[v][j] - mean) * rstd;
-          const float d = dyg[v][j];
-          xh[v][j] = xhat;
-          dg[v][j] += d * xhat;
-          db[v][j] += d;
-          const float dgm = d * gm[v][j];
-          dyg[v][j] = dgm;
-          red[0] += dgm;
-          red[1] += dgm * xhat;
+      for (int v = 0; v < NV; ++v) {
+        if (act[v]) {
+          unstage8<X_F32>(xring + st_read + (r * NV + v) * xstride, xh[r][v]);
+          unstage8<DY_F32>(yring + st_read + (r * NV + v) * ystride, dgm[r][v]);
         }
       }
     }
-    block_sum_n<2>(red, buf, phase);
-    const float s1 = red[0] * invD, s2 = red[1] * invD;
+    const int nvalid = rows - g * RPI;
+    if (nvalid < RPI) {  // ragged last group: rows past the end contribute exact zeros
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * blockDim.x + tid) * 8;
-      if (c < D) {
-        float o[8];
+      for (int r = 0; r < RPI; ++r) {
+        if (r >= nvalid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (dyg[v][j] - s1 - xh[v][j] * s2);
-        store8<DX_F32>(dx, row * D + c, o);
-        if (dx_drop != nullptr) {
-          const uint32_t keep = dropout_keep8(seed, offset, (uint64_t)(row * ld8 + (c >> 3)), drop_thr16);
+          for (int v = 0; v < NV; ++v)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * drop_scale : 0.f;
-          store8<false>(dx_drop, row * D + c, o);
-        }
-        if (want_dxsum) {
-          // column sums of the gradient that enters the preceding Linear (its bias gradient), taken on the
-          // bf16-rounded values so they equal a column sum of the stored tensor
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dxs[v][j] += (DX_F32 && dx_drop == nullptr) ? o[j] : __bfloat162float(__float2bfloat16(o[j]));
+            for (int j = 0; j < 8; ++j) {
+              xh[r][v][j] = 0.f;
+              dgm[r][v][j] = 0.f;
+            }
         }
       }
     }
+    st_read = (st_read + stage_bytes == ring_bytes) ? 0u : st_read + stage_bytes;
+    issue();  // refills the slot consumed one iteration ago
+    fetch_stats(g + gridDim.x);
+    float red[2 * RPI];
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      red[2 * r] = 0.f;
+      red[2 * r + 1] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (act[v]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xhat = fmaf(xh[r][v][j], rs[r], nb[r]);
+            const float d = dgm[r][v][j];
+            xh[r][v][j] = xhat;
+            dg[v][j] = fmaf(d, xhat, dg[v][j]);
+            db[v][j] += d;
+            const float t = d * gm[v][j];
+            dgm[r][v][j] = t;
+            red[2 * r] += t;
+            red[2 * r + 1] = fmaf(t, xhat, red[2 * r + 1]);
+          }
+        }
+      }
+    }
+    block_sum<2 * RPI>(red, scratch, phase, lane, warp);
+    auto emit = [&](auto full) {
+#pragma unroll
+      for (int r = 0; r < RPI; ++r) {
+        if (decltype(full)::value || r < nvalid) {
+          const float b1 = -red[2 * r] * invD * rs[r], b2 = -red[2 * r + 1] * invD * rs[r];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if (act[v]) {
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[r][v][j], b2, fmaf(dgm[r][v][j], rs[r], b1));
+              const int64_t e = (int64_t)r * D + v * vcols;
+              uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+              if (DX_F32) store8_f32(reinterpret_cast<float*>(og + e * OE), o);
+              else {
+                pk = pack8(o);
+                store8_bf16(reinterpret_cast<__nv_bfloat16*>(og + e * OE), pk);
+              }
+              if (dx_drop != nullptr) {
+                uint32_t rnd[4];
+                philox4x32_keyed(keys, offset, idx8 + (uint64_t)(r * ld8 + v * nthr), rnd);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = dropout_kept(rnd, j, drop_thr16) ? o[j] * drop_scale : 0.f;
+                pk = pack8(o);
+                store8_bf16(odg + e, pk);
+              }
+              if (want_dxsum) {
+                // column sums of the gradient that enters the preceding Linear (its bias gradient), taken on the
+                // bf16-rounded values so they equal a column sum of the stored tensor
+                if (!DX_F32 || dx_drop != nullptr) unpack8(pk, o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dxs[v][j] += o[j];
+              }
+            }
+          }
+        }
+      }
+    };
+    if (nvalid >= RPI) emit(BoolTag<true>());
+    else emit(BoolTag<false>());
+    og += gstep * OE;
+    if (dx_drop != nullptr) odg += gstep;
+    idx8 += idx8_step;
   }
   cp_async_wait<0>();
   float* pg = partial + (int64_t)blockIdx.x * 3 * D;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const int c = (v * blockDim.x + tid) * 8;
-    if (c < D) {
-      store8<true>(pg, c, dg[v]);
-      store8<true>(pg + D, c, db[v]);
-      if (want_dxsum) store8<true>(pg + 2 * D, c, dxs[v]);
+    if (act[v]) {
+      const int c = (v * nthr + tid) * 8;
+      store8_f32(pg + c, dg[v]);
+      store8_f32(pg + D + c, db[v]);
+      if (want_dxsum) store8_f32(pg + 2 * D + c, dxs[v]);
     }
   }
 }
@@ -401,27 +519,30 @@ extern "C" int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamm
   LSTC_CHECK_ARG(x && gamma && beta && y && mean && rstd, "lstc_layernorm_fwd: null pointer");
   LSTC_CHECK_ARG(D > 0 && D % 8 == 0 && D <= 8192, "lstc_layernorm_fwd: D=%lld must be a multiple of 8, <= 8192",
                  (long long)D);
+  LSTC_CHECK_ARG(rows >= 0 && rows < (int64_t)2000000000, "lstc_layernorm_fwd: rows=%lld out of range", (long long)rows);
   if (rows == 0) return LSTC_OK;
   int nv;
   const int threads = ln::threads_for(D, nv);
-  const int64_t iters = (rows + ln::RPI - 1) / ln::RPI;
-#define LSTC_LN_FWD_K(NV, A, B)                                                                       \
+  // rows per iteration / ring depth: sized so that the row registers (RPI*NV*8 floats) and the ring
+  // (NS*RPI*NV*threads*{16,32} B) stay within one CTA's budget
+#define LSTC_LN_FWD_K(NV, RPI, NS, A, B)                                                              \
   do {                                                                                                \
-    auto kern = ln::ln_fwd_kernel<NV, A, B>;                                                          \
-    const size_t smem = (size_t)ln::NSTG * ln::RPI * NV * threads * (A ? 32 : 16);                    \
+    auto kern = ln::ln_fwd_kernel<NV, RPI, NS, A, B>;                                                 \
+    const size_t smem = (size_t)NS * RPI * NV * threads * (A ? 32 : 16);                              \
+    const int64_t iters = (rows + RPI - 1) / RPI;                                                     \
     const int64_t grid = ln::resident_grid(kern, threads, smem, iters, 8);                            \
-    kern<<<(unsigned)grid, threads, smem, stream>>>(x, gamma, beta, y, mean, rstd, rows, (int)D, eps); \
+    kern<<<(unsigned)grid, threads, smem, stream>>>(x, gamma, beta, y, mean, rstd, (int)rows, (int)D, eps); \
   } while (0)
-#define LSTC_LN_FWD(NV)                                         \
-  do {                                                          \
-    if (x_is_f32 && y_is_f32) LSTC_LN_FWD_K(NV, true, true);    \
-    else if (x_is_f32) LSTC_LN_FWD_K(NV, true, false);          \
-    else if (y_is_f32) LSTC_LN_FWD_K(NV, false, true);          \
-    else LSTC_LN_FWD_K(NV, false, false);                       \
+#define LSTC_LN_FWD(NV, RPI_BF, NS_BF, RPI_F32, NS_F32)                       \
+  do {                                                                        \
+    if (x_is_f32 && y_is_f32) LSTC_LN_FWD_K(NV, RPI_F32, NS_F32, true, true); \
+    else if (x_is_f32) LSTC_LN_FWD_K(NV, RPI_F32, NS_F32, true, false);       \
+    else if (y_is_f32) LSTC_LN_FWD_K(NV, RPI_BF, NS_BF, false, true);         \
+    else LSTC_LN_FWD_K(NV, RPI_BF, NS_BF, false, false);                      \
   } while (0)
-  if (nv == 1) LSTC_LN_FWD(1);
-  else if (nv == 2) LSTC_LN_FWD(2);
-  else LSTC_LN_FWD(4);
+  if (nv == 1) LSTC_LN_FWD(1, 4, 6, 2, 4);  // measured on B200 at 62720 x 2048: 4 rows x 6 stages beats 4x4, 2x4, 2x8
+  else if (nv == 2) LSTC_LN_FWD(2, 2, 3, 2, 3);
+  else LSTC_LN_FWD(4, 2, 2, 2, 2);
 #undef LSTC_LN_FWD
 #undef LSTC_LN_FWD_K
   LSTC_CHECK_LAUNCH();
@@ -441,6 +562,7 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
                  "lstc_layernorm_bwd: null pointer");
   LSTC_CHECK_ARG(D > 0 && D % 8 == 0 && D <= 8192, "lstc_layernorm_bwd: D=%lld must be a multiple of 8, <= 8192",
                  (long long)D);
+  LSTC_CHECK_ARG(rows >= 0 && rows < (int64_t)2000000000, "lstc_layernorm_bwd: rows=%lld out of range", (long long)rows);
   LSTC_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "lstc_layernorm_bwd: drop_p out of range");
   if (rows == 0) {
     LSTC_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, D * sizeof(float), stream));
@@ -455,28 +577,29 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
   const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const uint32_t thr = dropout_threshold16(drop_p);
   float* partial = (float*)workspace;
-#define LSTC_LN_BWD_K(NV, A, B, C)                                                                             \
+#define LSTC_LN_BWD_K(NV, RPI, NS, A, B, C)                                                                    \
   do {                                                                                                         \
-    auto kern = ln::ln_bwd_kernel<NV, A, B, C>;                                                                \
-    const size_t smem = (size_t)ln::NSTG * NV * threads * ((B ? 32 : 16) + (A ? 32 : 16));                     \
-    grid = ln::resident_grid(kern, threads, smem, rows, 8);                                                    \
+    auto kern = ln::ln_bwd_kernel<NV, RPI, NS, A, B, C>;                                                       \
+    const size_t smem = (size_t)NS * RPI * NV * threads * ((B ? 32 : 16) + (A ? 32 : 16));                     \
+    grid = ln::resident_grid(kern, threads, smem, (rows + RPI - 1) / RPI, 8);                                  \
     kern<<<(unsigned)grid, threads, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dd, dscale, thr, seed, offset, \
-                                                 partial, dxsum != nullptr ? 1 : 0, rows, (int)D);             \
+                                                 partial, dxsum != nullptr ? 1 : 0, (int)rows, (int)D);             \
   } while (0)
-#define LSTC_LN_BWD(NV)                                             \
-  do {                                                              \
-    if (dy_is_f32 && x_is_f32 && dx_is_f32) LSTC_LN_BWD_K(NV, true, true, true);         \
-    else if (dy_is_f32 && !x_is_f32 && !dx_is_f32) LSTC_LN_BWD_K(NV, true, false, false); \
-    else if (!dy_is_f32 && x_is_f32 && dx_is_f32) LSTC_LN_BWD_K(NV, false, true, true);   \
-    else if (!dy_is_f32 && !x_is_f32 && !dx_is_f32) LSTC_LN_BWD_K(NV, false, false, false); \
-    else {                                                          \
-      set_last_error("lstc_layernorm_bwd: unsupported dtype combination (dx must match x)"); \
-      return LSTC_ERR_UNSUPPORTED;                                  \
-    }                                                               \
+#define LSTC_LN_BWD(NV, RPI_BF, NS_BF, RPI_MIX, NS_MIX, RPI_F32, NS_F32)                                       \
+  do {                                                                                                         \
+    if (dy_is_f32 && x_is_f32 && dx_is_f32) LSTC_LN_BWD_K(NV, RPI_F32, NS_F32, true, true, true);              \
+    else if (dy_is_f32 && !x_is_f32 && !dx_is_f32) LSTC_LN_BWD_K(NV, RPI_MIX, NS_MIX, true, false, false);     \
+    else if (!dy_is_f32 && x_is_f32 && dx_is_f32) LSTC_LN_BWD_K(NV, RPI_F32, NS_F32, false, true, true);       \
+    else if (!dy_is_f32 && !x_is_f32 && !dx_is_f32) LSTC_LN_BWD_K(NV, RPI_BF, NS_BF, false, false, false);     \
+    else {                                                                                                     \
+      set_last_error("lstc_layernorm_bwd: unsupported dtype combination (dx must match x)");                   \
+      return LSTC_ERR_UNSUPPORTED;                                                                             \
+    }                                                                                                          \
   } while (0)
-  if (nv == 1) LSTC_LN_BWD(1);
-  else if (nv == 2) LSTC_LN_BWD(2);
-  else LSTC_LN_BWD(4);
+  // measured on B200 at 62720 x 2048: 2 rows x 4 stages (120 registers, 2 CTAs / SM) beats 4x3, 4x2, 1x4 and 3 CTAs / SM
+  if (nv == 1) LSTC_LN_BWD(1, 2, 4, 2, 4, 2, 3);
+  else if (nv == 2) LSTC_LN_BWD(2, 1, 4, 1, 4, 1, 4);
+  else LSTC_LN_BWD(4, 1, 2, 1, 2, 1, 2);
 #undef LSTC_LN_BWD
 #undef LSTC_LN_BWD_K
   LSTC_CHECK_LAUNCH();

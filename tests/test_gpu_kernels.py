@@ -144,7 +144,8 @@ def test_gemm_rejects_cpu_and_bad_args(ops):
 
 
 # ------------------------------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("rows,D", [(1, 2048), (49, 2048), (333, 1024), (62, 4096), (17, 3072), (5, 8)])
+@pytest.mark.parametrize("rows,D", [(1, 2048), (49, 2048), (333, 1024), (62, 4096), (17, 3072), (5, 8), (11, 8192),
+                                    (7, 6144), (2051, 2048)])
 @pytest.mark.parametrize("xdt,ydt", [(BF16, BF16), (F32, F32), (BF16, F32)])
 def test_layernorm_fwd(ops, rows, D, xdt, ydt):
     x = (_rand((rows, D), 2.0, 20, F32) + 0.5).to(xdt)
@@ -159,7 +160,8 @@ def test_layernorm_fwd(ops, rows, D, xdt, ydt):
     assert_close("ln rstd", rstd, 1.0 / torch.sqrt(x.float().var(-1, unbiased=False) + 1e-6), rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("rows,D", [(1, 2048), (490, 2048), (333, 1024), (62, 4096), (3000, 2048)])
+@pytest.mark.parametrize("rows,D", [(1, 2048), (490, 2048), (333, 1024), (62, 4096), (3000, 2048), (11, 8192), (7, 6144),
+                                    (2051, 2048), (6, 64)])
 @pytest.mark.parametrize("dt", [BF16, F32])
 def test_layernorm_bwd(ops, rows, D, dt):
     x = (_rand((rows, D), 2.0, 23, F32) + 0.5).to(dt)
@@ -187,6 +189,34 @@ def test_layernorm_bwd_dropout_output(ops):
     dx, dx_drop, _, _ = ops.layernorm_bwd(dy, x, g, mean, rstd, dropout=drop)
     keep = ops.dropout_mask(rows, D, drop).float()
     assert_close("ln bwd dx_drop", dx_drop, dx.float() * keep / (1 - p), rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows", [3, 490, 2051])
+@pytest.mark.parametrize("dy_dt", [BF16, F32])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_layernorm_bwd_dxsum_and_mixed_dtypes(ops, rows, dy_dt, p):
+    """dy fp32 | bf16 with bf16 x (the last block's LayerNorm hands an fp32 gradient back), the column sums of the
+    tensor the preceding Linear receives (its bias gradient) and the dropout copy, ragged row groups included."""
+    D = 2048
+    x = _rand((rows, D), 1.5, 40)
+    g = _rand((D,), 1.0, 41, F32) + 1.0
+    b = _rand((D,), 1.0, 42, F32)
+    dy = _rand((rows, D), 1.0, 43, F32).to(dy_dt)
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), g, b, eps=1e-6).backward(dy.float())
+    _, mean, rstd = ops.layernorm_fwd(x, g, b)
+    drop = (p, 7, 3) if p > 0 else (0.0, 0, 0)
+    dx, dx_drop, dgamma, dbeta, dxsum = ops.layernorm_bwd(dy, x, g, mean, rstd, dropout=drop, want_dxsum=True)
+    assert dx.dtype == BF16
+    assert_close("ln bwd mixed dx", dx, xr.grad, rtol=2e-2, atol=2e-2)
+    src = dx
+    if p > 0:
+        keep = ops.dropout_mask(rows, D, drop).float()
+        assert_close("ln bwd mixed dx_drop", dx_drop, dx.float() * keep / (1 - p), rtol=1e-2, atol=1e-3)
+        src = dx_drop
+    else:
+        assert dx_drop is None
+    assert_close("ln bwd dxsum", dxsum, src.float().sum(0), rtol=1e-3, atol=1e-3 * math.sqrt(rows) + 1e-3)
 
 
 # ------------------------------------------------------------------------------------------ attention
