@@ -323,7 +323,9 @@ def test_forward_cls_fast_path_equals_full_path(M, L, name):
     r0, p0, xg0, g0 = run(False)
     r1, p1, xg1, g1 = run(True)
     tensor_close(f"{name} cls rows", r1, r0, rel_l2=1e-2, p999=3e-2, max_rel=6e-2)
-    probs_close(f"{name} cls probs", p1, p0, max_abs=3e-3, mean_abs=1e-3)
+    # two bf16 evaluation orders of the same math: the bound is the bf16 floor the reference itself shows under
+    # autocast (3.4e-3 max / 8e-4 mean at this shape, oracle/measure_bf16_floor.py) with a 2x margin
+    probs_close(f"{name} cls probs", p1, p0, max_abs=7e-3, mean_abs=2e-3)
     assert set(g0) == set(g1)
     # the two paths round differently (bf16 tensor-core P.V vs fp32 SIMT in the CLS kernel); gradients amplify that
     # like they amplify any bf16 rounding (see the calibration in the module docstring)
