@@ -9,6 +9,7 @@ scripts themselves keep working unmodified on lstc_vad_b200.models.
 from __future__ import annotations
 
 import math
+import os
 import types
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -223,18 +224,16 @@ class GraphedTrainStep:
     Dropout: a graph bakes every kernel's (seed, offset) by value, so a device-resident step counter is registered
     with the library (`lstc_set_rng_step`) and bumped INSIDE the graph; every replay therefore draws fresh masks.
     The bf16 weight copies are re-cast inside the graph as well (the cache is invalidated right before capture), so
-    an in-graph optimizer step is seen by the next replay.  Single-GPU only (the bucketed all-reduce of the
-    data-parallel path stays eager)."""
+    an in-graph optimizer step is seen by the next replay.  With world_size > 1 the score all-gather and the bucketed
+    side-stream all-reduces are captured too (NCCL collectives are graph-capturable); every rank must construct and
+    replay its graph in lock-step, and the process should exit without destroying the process group while a graph
+    that holds captured collectives is alive."""
 
     RNG_STRIDE = 4096  # > number of dropout sites per step
 
     def __init__(self, step: "TrainStep", feats: torch.Tensor, labs: Optional[torch.Tensor], local_batch: int,
                  warmup: int = 3):
         from . import _lib
-        if step.world != 1:
-            # capturing the NCCL side-stream all-reduce works but gains ~1 % and process-group teardown after a
-            # captured collective hung in testing: the data-parallel path stays eager
-            raise RuntimeError("GraphedTrainStep supports world_size 1 only")
         # Autograd's AccumulateGrad nodes remember the stream of the forward that created them and live as long as any
         # autograd graph of an earlier (eager, default-stream) step is referenced; such a node would make the legacy
         # stream wait on the capturing stream.  Drop dead graphs so the side-stream warm-up below re-creates the nodes.
@@ -259,7 +258,8 @@ class GraphedTrainStep:
         Fn.invalidate_weight_cache()
         step.zero_grad()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if step.world > 1 else "global"):
             self.rng_counter += self.RNG_STRIDE
             self.terms = step.forward_backward(self.static_feats, self.static_labs, local_batch)
 
@@ -312,6 +312,9 @@ class BucketedGradReducer:
         self.stream = comm_stream or torch.cuda.Stream()
         self._active = False
         self._skip: set = set()
+        # "overlap": launch a bucket's all-reduce as soon as its last gradient lands (default);
+        # "tail": launch all buckets after backward (no SM contention between NCCL and the persistent GEMMs)
+        self.mode = os.environ.get("LSTC_DP_REDUCE", "overlap")
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
                 p.register_post_accumulate_grad_hook(self._make_hook(bi))
@@ -351,7 +354,7 @@ class BucketedGradReducer:
             if not self._active:
                 return
             self.pending[bi] -= 1
-            if self.pending[bi] == 0:
+            if self.pending[bi] == 0 and self.mode != "tail":
                 self._launch(bi)
         return hook
 
@@ -390,6 +393,8 @@ class BucketedGradReducer:
                 unused = [p for p in self.buckets[bi] if p.grad is None]
                 self.mark_unused(unused)
                 self.pending[bi] = 0
+                self._launch(bi)
+            elif self.mode == "tail":
                 self._launch(bi)
         torch.cuda.current_stream().wait_stream(self.stream)
         self._active = False
