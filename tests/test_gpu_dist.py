@@ -40,11 +40,29 @@ def _worker(rank, world, port, out):
     torch.cuda.synchronize()
     ce = terms["ce"].detach().clone()
     dist.all_reduce(ce)
+    named = list(step.encoder.named_parameters()) + [("head." + n, p) for n, p in step.head.named_parameters()]
+    grads = {n: p.grad.detach().cpu().clone() for n, p in named if p.grad is not None}
+    mil = terms["mil"].item()
+    del terms
+    # the same data-parallel step replayed as a CUDA graph (score all-gather + bucketed all-reduces captured)
+    from lstc_vad_b200.harness import GraphedTrainStep
+    gstep = GraphedTrainStep(step, feats[sel].contiguous(), labs[sel].contiguous(), Bl, warmup=2)
+    gterms = gstep()
+    gterms = gstep()
+    torch.cuda.synchronize()
+    graph_err = 0.0
+    for n, p in named:
+        if p.grad is not None:
+            r = grads[n].float()
+            graph_err = max(graph_err, ((p.grad.detach().cpu().float() - r).norm() / r.norm().clamp_min(1e-12)).item())
+    graph_mil = gterms["mil"].item()
+    gstep.close()
     if rank == 0:
-        grads = {n: p.grad.detach().cpu().clone() for n, p in list(step.encoder.named_parameters()) +
-                 [("head." + n, p) for n, p in step.head.named_parameters()] if p.grad is not None}
-        torch.save(dict(mil=terms["mil"].item(), ce=ce.item(), grads=grads), out)
-    dist.destroy_process_group()
+        torch.save(dict(mil=mil, ce=ce.item(), grads=grads, graph_err=graph_err, graph_mil=graph_mil), out)
+    # graphs with captured collectives are alive: leave without tearing the communicator down
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -75,3 +93,6 @@ def test_two_gpu_data_parallel_step_equals_single_gpu(tmp_path):
         assert err < 1e-3, (n, err.item())
         checked += 1
     assert checked > 20
+    # CUDA-graph replay of the data-parallel step: same kernels, same collectives
+    assert abs(got["graph_mil"] - got["mil"]) < 1e-6
+    assert got["graph_err"] < 1e-3, got["graph_err"]
