@@ -362,7 +362,7 @@ __device__ __forceinline__ void store_chunk(const float (&acc)[8][4], __nv_bfloa
 // Forward
 // ==========================================================================================
 template <int LP, int DK, int NS>
-__global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p_in) {
+__global__ void __launch_bounds__(LP / 16 * 32, LP > 64 ? 3 : 1) attn_fwd_kernel(const Params p_in) {
   Params p = p_in;
   p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(LP / 16 * 32) attn_fwd_kernel(const Params p_i
 // Backward
 // ==========================================================================================
 template <int LP, int DK, int NS>
-__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 1) attn_bwd_kernel(const Params p_in) {
+__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2) attn_bwd_kernel(const Params p_in) {
   Params p = p_in;
   p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;

@@ -53,10 +53,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--L", type=int, default=49, help="tokens per window incl. CLS (49 SHT, 19 UCF, 81 UBnormal, 17 STN)")
+    ap.add_argument("--W", type=int, default=1280)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    W, L, H, dk, D = 1280, 49, 8, 256, 2048
+    W, L, H, dk, D = args.W, args.L, 8, 256, 2048
     rows = W * L
     peak = hbm_peak()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
