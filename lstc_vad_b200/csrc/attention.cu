@@ -16,6 +16,10 @@
 // accumulation, softmax by quad shuffles, dropout regenerated from Philox, rel-pos bias read from a dense
 // [H,L,L] table, its gradient accumulated in registers across the windows of the CTA (one atomic flush).
 // Warp w of the CTA owns query rows [16w, 16w+16) (and key rows [16w, 16w+16) of dK / dV).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/lstc_vad_b200.h"
 
@@ -65,6 +69,47 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+
+// ---- mbarrier + TMA (tile loads of the TMA variant of the stage ring) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a broken pipeline traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("lstc attention: mbarrier wait timed out (block %d,%d thread %d)\n", (int)blockIdx.x, (int)blockIdx.y,
+             (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+// [LP x 64] box of window c2 starting at column c0 (row c1 = 0; rows >= L are out of bounds -> zero-filled)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int32_t c0,
+                                            int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 // byte offset of 16-byte chunk c16 (0..7) of row r inside a [rows][64] bf16 chunk tile (128-byte rows); the chunk
@@ -248,7 +293,13 @@ __device__ __forceinline__ float dropped(float pr, const uint32_t (&keep)[2], in
 // cp.async stage ring shared by both kernels.  A stage holds two [LP x 64] chunk tiles.
 //   PHASES x NC stages per window; phase ph, chunk c loads tile0 / tile1 from the tensors listed below.
 // ------------------------------------------------------------------------------------------
-template <int LP, int DK, int NS, bool BWD>
+// Two interchangeable ways of filling a stage:
+//   TMA = false: every thread issues its 4 cp.async pieces per tile (TileCopy), completion by cp.async groups;
+//   TMA = true : thread 0 issues one cp.async.bulk.tensor per tile (3-D map [W][L][cols], box [1][LP][64],
+//                SWIZZLE_128B = the ct_off() pattern, rows >= L zero-filled by the hardware), completion on one
+//                mbarrier per stage.  The other 127 threads execute no load instructions at all.
+// In both variants a stage is recycled behind the CTA-wide barrier of acquire().
+template <int LP, int DK, int NS, bool BWD, bool TMA>
 struct Ring {
   static constexpr int NC = DK / 64;
   static constexpr int CT = LP * 128;
@@ -266,52 +317,92 @@ struct Ring {
   const __nv_bfloat16 *gq, *gd;
   int64_t wstep_q, wstep_d, kstep_q, kstep_d;
   int HD;
+  // TMA variant
+  const CUtensorMap *tq, *td;
+  uint32_t bars;          // NS mbarriers (8 bytes each)
+  uint32_t bar_p, bar_c;  // barrier offsets of the producer / consumer stage
+  uint32_t par_c;         // phase parity the consumer waits for
+  int col0;
 
-  __device__ Ring(const Params& p_, uint32_t base_, int h) : p(p_), base(base_) {
+  __device__ Ring(const Params& p_, uint32_t base_, uint32_t bars_, int h, const CUtensorMap* tq_,
+                  const CUtensorMap* td_)
+      : p(p_), base(base_), tq(tq_), td(td_), bars(bars_) {
     const int W = (int)p.W;
     n_it = ((int)blockIdx.x < W) ? (W - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    cp.init(p.L);
     w_p = blockIdx.x;
     ph_p = 0; c_p = 0;
     off_p = 0; off_c = (NS - 1) * STAGE;  // off_c is advanced to 0 by the first acquire()
+    bar_p = 0; bar_c = (NS - 1) * 8; par_c = 1;  // parity flips to 0 when the consumer wraps to slot 0
     HD = p.H * DK;
-    const int r0 = threadIdx.x >> 3, c16 = threadIdx.x & 7;
-    gq = p.qkv + ((int64_t)w_p * p.L + r0) * p.ld + h * DK + c16 * 8;
-    wstep_q = (int64_t)gridDim.x * p.L * p.ld;
-    kstep_q = (int64_t)TileCopy<LP>::RSTEP * p.ld;
-    gd = nullptr; wstep_d = 0; kstep_d = 0;
-    if (BWD) {
-      gd = p.dout + ((int64_t)w_p * p.L + r0) * p.ld_dout + h * DK + c16 * 8;
-      wstep_d = (int64_t)gridDim.x * p.L * p.ld_dout;
-      kstep_d = (int64_t)TileCopy<LP>::RSTEP * p.ld_dout;
+    col0 = h * DK;
+    gq = nullptr; gd = nullptr; wstep_q = 0; kstep_q = 0; wstep_d = 0; kstep_d = 0;
+    if (!TMA) {
+      cp.init(p.L);
+      const int r0 = threadIdx.x >> 3, c16 = threadIdx.x & 7;
+      gq = p.qkv + ((int64_t)w_p * p.L + r0) * p.ld + h * DK + c16 * 8;
+      wstep_q = (int64_t)gridDim.x * p.L * p.ld;
+      kstep_q = (int64_t)TileCopy<LP>::RSTEP * p.ld;
+      if (BWD) {
+        gd = p.dout + ((int64_t)w_p * p.L + r0) * p.ld_dout + h * DK + c16 * 8;
+        wstep_d = (int64_t)gridDim.x * p.L * p.ld_dout;
+        kstep_d = (int64_t)TileCopy<LP>::RSTEP * p.ld_dout;
+      }
+    } else {
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(bars + s * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
     }
   }
   __device__ __forceinline__ uint32_t cur(int which) const { return base + off_c + which * CT; }
 
+  // one stage: tile 0 (and tile 1 unless `single`) from tensor a / b (0 = qkv, 1 = dout) at column offsets ca / cb
+  __device__ __forceinline__ void issue_tma(bool single, int ta, int ca, int tb, int cb) {
+    const uint32_t bar = bars + bar_p, t0 = base + off_p;
+    mbar_arrive_expect_tx(bar, single ? CT : 2 * CT);
+    tma_load_3d(t0, ta ? td : tq, bar, ca, 0, w_p);
+    if (!single) tma_load_3d(t0 + CT, tb ? td : tq, bar, cb, 0, w_p);
+  }
+
   __device__ __forceinline__ void issue_next() {
     if (w_p < (int)p.W) {
-      const __nv_bfloat16* q = gq + c_p * 64;
-      const uint32_t t0 = base + off_p, t1 = t0 + CT;
-      if (!BWD) {
-        if (ph_p == 0) {
-          cp.load(t0, q, kstep_q, p.qkv);
-          cp.load(t1, q + HD, kstep_q, p.qkv);
+      if (TMA) {
+        const int cq = col0 + c_p * 64;
+        if (!BWD) {
+          if (ph_p == 0) issue_tma(false, 0, cq, 0, cq + HD);
+          else issue_tma(true, 0, cq + 2 * HD, 0, 0);
         } else {
-          cp.load(t0, q + 2 * HD, kstep_q, p.qkv);
+          if (ph_p == 0) issue_tma(false, 0, cq, 0, cq + HD);
+          else if (ph_p == 1) issue_tma(false, 1, cq, 0, cq + 2 * HD);
+          else if (ph_p == 2) issue_tma(false, 0, cq + HD, 0, cq);  // K_c, Q_c
+          else issue_tma(true, 1, cq, 0, 0);
         }
       } else {
-        const __nv_bfloat16* d_o = gd + c_p * 64;
-        if (ph_p == 0) {
-          cp.load(t0, q, kstep_q, p.qkv);
-          cp.load(t1, q + HD, kstep_q, p.qkv);
-        } else if (ph_p == 1) {
-          cp.load(t0, d_o, kstep_d, p.qkv);
-          cp.load(t1, q + 2 * HD, kstep_q, p.qkv);
-        } else if (ph_p == 2) {
-          cp.load(t0, q + HD, kstep_q, p.qkv);  // K_c
-          cp.load(t1, q, kstep_q, p.qkv);       // Q_c
+        const __nv_bfloat16* q = gq + c_p * 64;
+        const uint32_t t0 = base + off_p, t1 = t0 + CT;
+        if (!BWD) {
+          if (ph_p == 0) {
+            cp.load(t0, q, kstep_q, p.qkv);
+            cp.load(t1, q + HD, kstep_q, p.qkv);
+          } else {
+            cp.load(t0, q + 2 * HD, kstep_q, p.qkv);
+          }
         } else {
-          cp.load(t0, d_o, kstep_d, p.qkv);
+          const __nv_bfloat16* d_o = gd + c_p * 64;
+          if (ph_p == 0) {
+            cp.load(t0, q, kstep_q, p.qkv);
+            cp.load(t1, q + HD, kstep_q, p.qkv);
+          } else if (ph_p == 1) {
+            cp.load(t0, d_o, kstep_d, p.qkv);
+            cp.load(t1, q + 2 * HD, kstep_q, p.qkv);
+          } else if (ph_p == 2) {
+            cp.load(t0, q + HD, kstep_q, p.qkv);  // K_c
+            cp.load(t1, q, kstep_q, p.qkv);       // Q_c
+          } else {
+            cp.load(t0, d_o, kstep_d, p.qkv);
+          }
         }
       }
       if (++c_p == NC) {
@@ -319,24 +410,40 @@ struct Ring {
         if (++ph_p == NPH) {
           ph_p = 0;
           w_p += gridDim.x;
-          gq += wstep_q;
-          if (BWD) gd += wstep_d;
+          if (!TMA) {
+            gq += wstep_q;
+            if (BWD) gd += wstep_d;
+          }
         }
       }
       off_p = (off_p + STAGE == NS * STAGE) ? 0u : off_p + STAGE;
+      bar_p = (bar_p + 8 == NS * 8) ? 0u : bar_p + 8;
     }
-    cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
+    if (!TMA) cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
   }
   __device__ __forceinline__ void prologue() {
+    if (!TMA || threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < NS - 1; ++i) issue_next();
+      for (int i = 0; i < NS - 1; ++i) issue_next();
+    }
   }
   // Makes the next stage resident and visible to all warps (-> cur()), then refills the slot consumed one step earlier.
   __device__ __forceinline__ void acquire() {
-    cp_async_wait<NS - 2>();
-    __syncthreads();
     off_c = (off_c + STAGE == NS * STAGE) ? 0u : off_c + STAGE;
-    issue_next();
+    if (TMA) {
+      bar_c = (bar_c + 8 == NS * 8) ? 0u : bar_c + 8;
+      if (bar_c == 0) par_c ^= 1u;
+      mbar_wait(bars + bar_c, par_c);
+      __syncthreads();
+      if (threadIdx.x == 0) issue_next();
+    } else {
+      cp_async_wait<NS - 2>();
+      __syncthreads();
+      issue_next();
+    }
+  }
+  __device__ __forceinline__ void drain() {
+    if (!TMA) cp_async_wait<0>();
   }
 };
 
@@ -361,19 +468,20 @@ __device__ __forceinline__ void store_chunk(const float (&acc)[8][4], __nv_bfloa
 // ==========================================================================================
 // Forward
 // ==========================================================================================
-template <int LP, int DK, int NS>
-__global__ void __launch_bounds__(LP / 16 * 32, LP > 64 ? 3 : 1) attn_fwd_kernel(const Params p_in) {
+template <int LP, int DK, int NS, bool TMA>
+__global__ void __launch_bounds__(LP / 16 * 32, LP > 64 ? 3 : 4)
+attn_fwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv) {
   Params p = p_in;
   p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
-  using R = Ring<LP, DK, NS, false>;
+  using R = Ring<LP, DK, NS, false, TMA>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t s0 = smem_u32(smem);
+  const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const int h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = warp * 16;
-  R ring(p, s0, h);
+  R ring(p, s0, s0 + NS * R::STAGE, h, &tm_qkv, nullptr);
   ring.prologue();
   for (int it = 0; it < ring.n_it; ++it) {
     const int64_t w = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -422,22 +530,23 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP > 64 ? 3 : 1) attn_fwd_kernel
       store_chunk(o, obase + c * 64, p.ld_out, m0, p.L, lane);
     }
   }
-  cp_async_wait<0>();
+  ring.drain();
   (void)NW;
 }
 
 // ==========================================================================================
 // Backward
 // ==========================================================================================
-template <int LP, int DK, int NS>
-__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2) attn_bwd_kernel(const Params p_in) {
+template <int LP, int DK, int NS, bool TMA>
+__global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2)
+attn_bwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do) {
   Params p = p_in;
   p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
   constexpr int PP = (LP + 8) * 2;  // padded row pitch (bytes) of the bf16 Pd / dS tiles
-  using R = Ring<LP, DK, NS, true>;
+  using R = Ring<LP, DK, NS, true, TMA>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t s0 = smem_u32(smem);
+  const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const int h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -450,7 +559,7 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2) attn_bwd_kerne
   for (int n = 0; n < NT; ++n) {
     dbacc[n][0] = 0.f; dbacc[n][1] = 0.f; dbacc[n][2] = 0.f; dbacc[n][3] = 0.f;
   }
-  R ring(p, s0, h);
+  R ring(p, s0, sDS + LP * PP, h, &tm_qkv, &tm_do);
   ring.prologue();
   for (int it = 0; it < ring.n_it; ++it) {
     const int64_t w = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -555,7 +664,7 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2) attn_bwd_kerne
       }
     }
   }
-  cp_async_wait<0>();
+  ring.drain();
 
   if (p.dbias != nullptr) {
 #pragma unroll
@@ -572,18 +681,79 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2) attn_bwd_kerne
 }
 
 // ------------------------------------------------------------------------------------------
-template <int LP, int DK, bool BWD>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+// 3-D bf16 map over [W][L][cols] (row pitch ld elements, window pitch L*ld), box [1][box_rows][64], SWIZZLE_128B,
+// zero fill out of bounds (rows L..box_rows-1 of a window)
+static int make_tmap3d(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t L, int64_t W, int64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return LSTC_ERR_DRIVER;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)W};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {64u, box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("attention: cuTensorMapEncodeTiled failed (CUresult %d) cols=%lld L=%lld W=%lld ld=%lld", (int)r,
+                   (long long)cols, (long long)L, (long long)W, (long long)ld);
+    return LSTC_ERR_DRIVER;
+  }
+  return LSTC_OK;
+}
+
+static bool use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LSTC_ATTN_TMA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int LP, int DK, bool BWD, bool TMA>
 static int launch(const Params& p, cudaStream_t stream) {
   constexpr int NS = 3;
   constexpr int NW = LP / 16;
   constexpr int STAGE = 2 * LP * 128;
-  constexpr int SMEM = NS * STAGE + (BWD ? 2 * LP * (LP + 8) * 2 : 0);
+  // + 1024: alignment slack of the swizzled tiles, + NS mbarriers
+  constexpr int SMEM = NS * STAGE + (BWD ? 2 * LP * (LP + 8) * 2 : 0) + 1024 + NS * 8;
   static bool attr_set[64] = {false};
   int dev = 0;
   LSTC_CHECK_CUDA(cudaGetDevice(&dev));
   static int CTAS_PER_SM = 0;  // resident CTAs per SM for this instantiation (occupancy API: smem + registers)
+  const int HD = p.H * DK;
+  CUtensorMap tq, td;
+  memset(&tq, 0, sizeof(tq));
+  memset(&td, 0, sizeof(td));
+  if (TMA) {
+    int rc = make_tmap3d(&tq, p.qkv, 3 * (int64_t)HD, p.L, p.W, p.ld, LP);
+    if (rc != LSTC_OK) return rc;
+    if (BWD) {
+      rc = make_tmap3d(&td, p.dout, HD, p.L, p.W, p.ld_dout, LP);
+      if (rc != LSTC_OK) return rc;
+    }
+  }
   if (BWD) {
-    auto kern = attn_bwd_kernel<LP, DK, NS>;
+    auto kern = attn_bwd_kernel<LP, DK, NS, TMA>;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -593,9 +763,9 @@ static int launch(const Params& p, cudaStream_t stream) {
     int64_t gx = ((int64_t)num_sms() * (CTAS_PER_SM > 0 ? CTAS_PER_SM : 1)) / p.H;
     if (gx < 1) gx = 1;
     if (gx > p.W) gx = p.W;
-    kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p);
+    kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p, tq, td);
   } else {
-    auto kern = attn_fwd_kernel<LP, DK, NS>;
+    auto kern = attn_fwd_kernel<LP, DK, NS, TMA>;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -605,7 +775,7 @@ static int launch(const Params& p, cudaStream_t stream) {
     int64_t gx = ((int64_t)num_sms() * (CTAS_PER_SM > 0 ? CTAS_PER_SM : 1)) / p.H;
     if (gx < 1) gx = 1;
     if (gx > p.W) gx = p.W;
-    kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p);
+    kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p, tq);
   }
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
@@ -614,8 +784,11 @@ static int launch(const Params& p, cudaStream_t stream) {
 template <int DK>
 static int dispatch_lp(bool bwd, const Params& p, cudaStream_t stream) {
   const int L = p.L;
-#define LSTC_ATTN_CASE(LPV) \
-  if (L <= LPV) return bwd ? launch<LPV, DK, true>(p, stream) : launch<LPV, DK, false>(p, stream);
+#define LSTC_ATTN_CASE(LPV)                                                                                   \
+  if (L <= LPV) {                                                                                             \
+    if (use_tma()) return bwd ? launch<LPV, DK, true, true>(p, stream) : launch<LPV, DK, false, true>(p, stream); \
+    return bwd ? launch<LPV, DK, true, false>(p, stream) : launch<LPV, DK, false, false>(p, stream);          \
+  }
   LSTC_ATTN_CASE(16)
   LSTC_ATTN_CASE(32)
   LSTC_ATTN_CASE(48)
