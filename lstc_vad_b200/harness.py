@@ -465,31 +465,50 @@ def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torc
     encoder.eval()
     head.eval()
     dev = next(encoder.parameters()).device
-    groups: Dict[int, List[Tuple[str, int, int, int, int]]] = {}
-    for key, feats in videos.items():
-        n = feats.shape[0]
-        for wi, (b, e, cover) in enumerate(video_windows(n, part_len, backshift)):
-            groups.setdefault(e - b, []).append((key, wi, b, e, cover))
-    win_scores: Dict[Tuple[str, int], float] = {}
     is_cls = isinstance(head, Classifier)
-    for n_clip_win, items in groups.items():
-        for s in range(0, len(items), max_windows):
-            chunk = items[s:s + max_windows]
-            batch = torch.stack([videos[k][b:e, :n_patch].reshape(-1, videos[k].shape[-1]) for k, _, b, e, _ in chunk])
-            xin = batch.to(dev, non_blocking=True).float()
+    T = part_len
+    # windows grouped by clip count: all full windows of a video are ONE view [n_full, T*N, D] of its feature tensor
+    # (no per-window slicing on the host); the ragged trailing window (short, or back-shifted to full length) joins
+    # the group of its own length
+    groups: Dict[int, List[Tuple[str, int, torch.Tensor]]] = {}   # clips per window -> [(key, first window index, [n, c*N, D])]
+    for key, feats in videos.items():
+        f = feats[:, :n_patch] if n_patch is not None else feats
+        n, D = f.shape[0], f.shape[-1]
+        n_full = n // T
+        if n_full:
+            groups.setdefault(T, []).append((key, 0, f[:n_full * T].reshape(n_full, -1, D)))
+        rem = n - n_full * T
+        if rem:
+            if backshift and n >= T:
+                groups.setdefault(T, []).append((key, n_full, f[n - T:n].reshape(1, -1, D)))
+            else:
+                groups.setdefault(rem, []).append((key, n_full, f[n_full * T:n].reshape(1, -1, D)))
+    win_scores: Dict[str, Dict[int, torch.Tensor]] = {}
+    for _, items in groups.items():
+        batch = torch.cat([x for _, _, x in items]).to(dev, non_blocking=True).float()
+        outs = []
+        for s0 in range(0, batch.shape[0], max_windows):
+            xin = batch[s0:s0 + max_windows]
             sc = head(encoder.forward_cls(xin) if cls_fast_path else encoder(xin)[:, 0, :])
             sc = sc[:, 1] if is_cls else sc[:, 0]
             if threshold is not None:
                 sc = losses.threshold_pseudo_labels(sc, threshold)
-            sc = sc.cpu()
-            for (k, wi, _, _, _), v in zip(chunk, sc.tolist()):
-                win_scores[(k, wi)] = v
+            outs.append(sc.float())
+        sc = torch.cat(outs).cpu()
+        off = 0
+        for key, w0, x in items:
+            win_scores.setdefault(key, {})[w0] = sc[off:off + x.shape[0]]
+            off += x.shape[0]
     result = {}
     for key, feats in videos.items():
-        vals = []
-        for wi, (_, _, cover) in enumerate(video_windows(feats.shape[0], part_len, backshift)):
-            vals += [win_scores[(key, wi)]] * cover
-        result[key] = torch.tensor(vals, dtype=torch.float32)
+        n = feats.shape[0]
+        n_full, rem = n // T, n % T
+        parts = []
+        if n_full:
+            parts.append(win_scores[key][0].repeat_interleave(T))
+        if rem:
+            parts.append(win_scores[key][n_full].repeat_interleave(rem))
+        result[key] = torch.cat(parts).to(torch.float32) if parts else torch.zeros(0)
     return result
 
 
@@ -595,3 +614,74 @@ class DeviceCorpus:
         feats = torch.cat(feats, dim=0)
         labs = losses.soft_clip_labels(torch.stack(abn_labels), batch_size, part_num, part_len).to(self.device)
         return feats, labs
+
+
+# --------------------------------------------------------------------------------------------------
+# one co-teaching round (README.md:21-36 of the reference: the four scripts run back to back)
+# --------------------------------------------------------------------------------------------------
+def synthetic_corpus(n_videos: int, n_patch: int, d_model: int, device, seed: int = 0, mean_clips: float = 50.0,
+                     min_clips: int = 24, max_clips: int = 160):
+    """(normal, abnormal) dicts {key: fp32 [n_clips, n_patch, d_model]} generated directly in HBM: half the videos
+    abnormal, clip counts log-normal around `mean_clips`, non-negative heavy-tailed
+    features like post-ReLU I3D activations."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    g = torch.Generator(device=device).manual_seed(seed)
+    normal, abnormal = {}, {}
+    for i in range(n_videos):
+        n = int(np.clip(rs.lognormal(np.log(mean_clips), 0.5), min_clips, max_clips))
+        f = torch.randn(n, n_patch, d_model, device=device, generator=g).abs_()
+        (abnormal if i % 2 else normal)[f"v{i:05d}"] = f
+    return normal, abnormal
+
+
+def co_teaching_round(corpus: "DeviceCorpus", stn: "TrainStep", ltn: "TrainStep", steps_per_epoch: Optional[int] = None,
+                      thr_stn: float = 0.9, thr_ltn: float = 0.65, rng=None, cls_fast_path: bool = False) -> Dict:
+    """STN epoch (MIL, Train/spatio_transformer_shanghaitech.py) -> STN pseudo labels, one clip per window, thr 0.9
+    (Train/pseudo_labels_generator_spatio.py) -> LTN epoch (MIL + CE on those labels,
+    Train/temporal_transformer_shanghaitech.py) -> LTN pseudo labels, thr 0.65
+    (Train/pseudo_labels_generator_temporal.py).  Both TrainSteps must own their optimizer.  Returns the two label
+    dicts, the last loss of each epoch and the wall-clock seconds of the four phases (device synchronised)."""
+    import time
+    import numpy as np
+    rng = rng if rng is not None else np.random.RandomState(0)
+    swl, lwl = stn.wl, ltn.wl
+    steps = steps_per_epoch or max(1, len(corpus) // swl.batch_size)
+    abn = dict(zip(corpus.abn_keys, corpus.abn))
+    t = {}
+
+    def clock(name, t0):
+        torch.cuda.synchronize()
+        t[name] = time.perf_counter() - t0
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    stn.encoder.train(); stn.head.train()
+    saved = corpus.pseudo
+    corpus.pseudo = None
+    for _ in range(steps):
+        feats, _ = corpus.sample_batch(swl.batch_size, swl.part_num, swl.part_len, "uniform", rng)
+        stn.zero_grad()
+        s_terms = stn.forward_backward(feats.view(-1, swl.n_patch, swl.d_model), None, swl.batch_size)
+    clock("stn_epoch", t0)
+    t0 = time.perf_counter()
+    stn_labels = score_videos(stn.encoder, stn.head, abn, part_len=1, threshold=thr_stn, n_patch=swl.n_patch,
+                              cls_fast_path=cls_fast_path)
+    clock("stn_labels", t0)
+    t0 = time.perf_counter()
+    corpus.pseudo = stn_labels
+    ltn.encoder.train(); ltn.head.train()
+    for _ in range(steps):
+        feats, labs = corpus.sample_batch(lwl.batch_size, lwl.part_num, lwl.part_len, "uniform", rng)
+        ltn.zero_grad()
+        l_terms = ltn.forward_backward(feats, labs, lwl.batch_size)
+    clock("ltn_epoch", t0)
+    t0 = time.perf_counter()
+    ltn_labels = score_videos(ltn.encoder, ltn.head, abn, part_len=lwl.part_len, threshold=thr_ltn, n_patch=lwl.n_patch,
+                              cls_fast_path=cls_fast_path)
+    clock("ltn_labels", t0)
+    corpus.pseudo = saved
+    n_clips = sum(int(v.shape[0]) for v in corpus.abn)
+    return dict(stn_labels=stn_labels, ltn_labels=ltn_labels, stn_loss=s_terms["loss"].item(), ltn_loss=l_terms["loss"].item(),
+                seconds=t, steps_per_epoch=steps, abnormal_clips=n_clips,
+                stn_label_windows=n_clips, ltn_label_windows=sum(-(-int(v.shape[0]) // lwl.part_len) for v in corpus.abn))

@@ -286,3 +286,32 @@ def test_device_corpus_sampler_gathers_the_reference_windows():
                 ref_lab.append(pseudo[keys[i]].reshape(-1)[ch])
     assert torch.equal(feats.cpu(), torch.cat(ref))
     assert torch.allclose(labs.cpu(), O.soft_labels(torch.stack(ref_lab), B, P, T))
+
+
+def test_co_teaching_round_runs_the_four_phases():
+    """STN epoch -> STN labels (one clip per window, thr 0.9) -> LTN epoch with CE on them -> LTN labels (thr 0.65):
+    label dicts have the reference's per-clip layout and thresholding, both models took optimizer steps."""
+    import numpy as np
+    from lstc_vad_b200.harness import DeviceCorpus, TrainStep, Workload, co_teaching_round, synthetic_corpus
+    dev = torch.device("cuda", 0)
+    swl = Workload("ct_stn", 256, 384, 3, 16, 4, 3, relative_pe=False, MHA_layerNorm=False, kind="stn", n_layers=1,
+                   n_head=2, d_k=64)
+    lwl = Workload("ct_ltn", 256, 512, 3, 16, 4, 3, n_layers=1, n_head=2, d_k=64)
+    normal, abnormal = synthetic_corpus(12, 16, 256, dev, seed=5, mean_clips=30.0, min_clips=14, max_clips=40)
+    corpus = DeviceCorpus(normal, abnormal, dev)
+    stn = TrainStep(swl, dev, seed=0, optimizer=True)
+    ltn = TrainStep(lwl, dev, seed=1, optimizer=True)
+    w_before = ltn.encoder.layer_stack[0].pos_ffn.w_1.weight.detach().clone()
+    out = co_teaching_round(corpus, stn, ltn, steps_per_epoch=2, thr_stn=0.5, thr_ltn=0.5, rng=np.random.RandomState(0))
+    assert set(out["stn_labels"]) == set(abnormal) == set(out["ltn_labels"])
+    for labels, thr in ((out["stn_labels"], 0.5), (out["ltn_labels"], 0.5)):
+        for k, v in labels.items():
+            assert v.shape == (abnormal[k].shape[0],) and v.dtype == torch.float32
+            assert bool(((v == 0) | (v > thr)).all())
+    # LTN labels are constant inside a window of part_len clips
+    k0 = sorted(abnormal)[0]
+    v = out["ltn_labels"][k0]
+    assert bool((v[0:3] == v[0]).all())
+    assert np.isfinite(out["stn_loss"]) and np.isfinite(out["ltn_loss"])
+    assert not torch.equal(w_before, ltn.encoder.layer_stack[0].pos_ffn.w_1.weight.detach())
+    assert set(out["seconds"]) == {"stn_epoch", "stn_labels", "ltn_epoch", "ltn_labels"}
