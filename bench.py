@@ -276,13 +276,16 @@ def main():
 
     # ---------------- end-to-end: pinned host inputs, H2D each step (double-buffered), D2H of the loss -------------
     copy_stream = torch.cuda.Stream()
-    loss_host = torch.empty(1, pin_memory=True)
+    loss_host = [torch.empty(1, pin_memory=True) for _ in range(2)]
 
     def run_e2e(bufs, run_step):
         """bufs[s] = (device feats, device labels) that step s % 2 reads; run_step(s) launches the step on them and
-        returns its loss terms.  The H2D copy of step i+1 (copy stream) overlaps the compute of step i."""
+        returns its loss terms.  The H2D copy of step i+1 (copy stream) overlaps the compute of step i; every step's
+        loss is read back to pinned host memory, and the host waits for the loss of step i-1 before it launches step
+        i+1 (asynchronous logging: one step of run-ahead, so the launch latency is not exposed between steps)."""
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
+        loss_read = [torch.cuda.Event() for _ in range(2)]
 
         def prefetch(i):
             s = i % 2
@@ -306,9 +309,13 @@ def main():
             torch.cuda.current_stream().wait_event(ready[s])
             out = run_step(s)
             consumed[s].record()
-            loss_host.copy_(out["loss"].detach().reshape(1), non_blocking=False)  # D2H read of the step's result
+            loss_host[s].copy_(out["loss"].detach().reshape(1), non_blocking=True)  # D2H read of the step's result
+            loss_read[s].record()
             out = None
+            if i >= 1:
+                loss_read[1 - s].synchronize()  # loss of step i-1 is on the host (the logger's value)
         t1.record()
+        loss_read[(steps - 1) % 2].synchronize()
         sync_all()
         return t0.elapsed_time(t1)
 

@@ -6,9 +6,9 @@
 // and its autograd backward.
 //
 // Grid = (window groups, heads).  A CTA owns one head and walks over windows.  Q/K/V (and dO) are
-// streamed through shared memory in [L x 64-column] chunk tiles by a multi-stage cp.async ring that runs
-// ahead across window boundaries, so HBM stays busy while the tensor cores work (the CTA never holds a
-// whole [L x dk] tile: ~56-74 KB of smem, 3-4 CTAs per SM):
+// streamed through shared memory in [L x 64-column] chunk tiles by a multi-stage TMA ring (cp.async.bulk.tensor,
+// one mbarrier per stage) that runs ahead across window boundaries, so HBM stays busy while the tensor cores work
+// (the CTA never holds a whole [L x dk] tile: ~49-114 KB of smem, 2-4 CTAs per SM):
 //   forward : S  += Q_c K_c^T (c = 0..dk/64-1) -> softmax / dropout in registers -> O_c = P V_c
 //   backward: S  += Q_c K_c^T ; dP += dO_c V_c^T -> P, dS in registers, bf16 copies in smem ->
 //             dQ_c = dS K_c ; dK_c = dS^T Q_c ; dV_c = P^T dO_c      (K, Q, dO chunks re-read through L2)
@@ -17,7 +17,6 @@
 // [H,L,L] table, its gradient accumulated in registers across the windows of the CTA (one atomic flush).
 // Warp w of the CTA owns query rows [16w, 16w+16) (and key rows [16w, 16w+16) of dK / dV).
 #include <cuda.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,15 +26,6 @@ namespace lstc {
 namespace attn {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -71,7 +61,7 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-// ---- mbarrier + TMA (tile loads of the TMA variant of the stage ring) ----
+// ---- mbarrier + TMA (tile loads of the stage ring) ----
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -132,36 +122,6 @@ struct Params {
   int64_t ld_out;
   float* probs;  // fwd optional
   float* dbias;  // bwd optional
-};
-
-// Per-thread copy pattern of a [LP x 64] chunk tile: the CTA's LP*2 threads move LP*8 16-byte pieces, i.e. every
-// thread moves exactly 4 -- column piece c16 = tid & 7 of rows r0 + k*LP/4 (k = 0..3, r0 = tid >> 3).  Everything
-// that does not depend on the tile (shared-memory offsets, validity of the 4 rows, the row step) is computed once
-// per kernel, so issuing a tile costs ~4 instructions per cp.async instead of re-deriving row / column / swizzle /
-// 64-bit address per piece.  Rows L..LP-1 are zero-filled (src-size 0).
-template <int LP>
-struct TileCopy {
-  static constexpr int RSTEP = LP / 4;
-  uint32_t dst[4];  // byte offsets inside a tile
-  int nvalid;       // pieces k < nvalid lie in rows < L
-
-  __device__ __forceinline__ void init(int L) {
-    const int r0 = threadIdx.x >> 3, c16 = threadIdx.x & 7;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = ct_off(r0 + k * RSTEP, c16);
-    nvalid = L > r0 ? (L - r0 + RSTEP - 1) / RSTEP : 0;
-    if (nvalid > 4) nvalid = 4;
-  }
-  // `src` = this thread's first piece (row r0, column piece c16 of the chunk); `kstep` = RSTEP rows in elements;
-  // `safe` = any valid global address (used for the zero-filled pieces)
-  __device__ __forceinline__ void load(uint32_t s_tile, const __nv_bfloat16* src, int64_t kstep,
-                                       const __nv_bfloat16* safe) const {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool v = k < nvalid;
-      cp_async16(s_tile + dst[k], v ? (const void*)(src + k * kstep) : (const void*)safe, v ? 16 : 0);
-    }
-  }
 };
 
 // acc (this warp's 16 rows x LP) += A_c[m0.., 0:64] * B_c[:, 0:64]^T, both chunk tiles [rows][64] (k contiguous)
@@ -293,13 +253,11 @@ __device__ __forceinline__ float dropped(float pr, const uint32_t (&keep)[2], in
 // cp.async stage ring shared by both kernels.  A stage holds two [LP x 64] chunk tiles.
 //   PHASES x NC stages per window; phase ph, chunk c loads tile0 / tile1 from the tensors listed below.
 // ------------------------------------------------------------------------------------------
-// Two interchangeable ways of filling a stage:
-//   TMA = false: every thread issues its 4 cp.async pieces per tile (TileCopy), completion by cp.async groups;
-//   TMA = true : thread 0 issues one cp.async.bulk.tensor per tile (3-D map [W][L][cols], box [1][LP][64],
-//                SWIZZLE_128B = the ct_off() pattern, rows >= L zero-filled by the hardware), completion on one
-//                mbarrier per stage.  The other 127 threads execute no load instructions at all.
-// In both variants a stage is recycled behind the CTA-wide barrier of acquire().
-template <int LP, int DK, int NS, bool BWD, bool TMA>
+// Stage ring filled by TMA: thread 0 issues one cp.async.bulk.tensor per tile (3-D map [W][L][cols], box
+// [1][LP][64], SWIZZLE_128B = the ct_off() pattern, rows >= L zero-filled by the hardware), completion on one mbarrier
+// per stage; the other threads execute no load instructions at all.  A stage is recycled behind the CTA-wide barrier
+// of acquire(), which also publishes the bf16 P / dS tiles of the backward.
+template <int LP, int DK, int NS, bool BWD>
 struct Ring {
   static constexpr int NC = DK / 64;
   static constexpr int CT = LP * 128;
@@ -309,20 +267,14 @@ struct Ring {
   const Params& p;
   uint32_t base;
   int n_it;  // windows this CTA processes
-  TileCopy<LP> cp;
-  // producer cursor (next stage to issue) and consumer slot, all maintained incrementally (no div / mod / 64-bit
-  // multiplies in the loop): gq / gd point at this thread's first piece of chunk 0 of Q / dO of window w_p
+  // producer cursor (next stage to issue; meaningful in thread 0 only) and consumer slot, maintained incrementally
   int w_p, ph_p, c_p;
   uint32_t off_p, off_c;  // byte offsets of the producer / consumer stage
-  const __nv_bfloat16 *gq, *gd;
-  int64_t wstep_q, wstep_d, kstep_q, kstep_d;
-  int HD;
-  // TMA variant
   const CUtensorMap *tq, *td;
   uint32_t bars;          // NS mbarriers (8 bytes each)
   uint32_t bar_p, bar_c;  // barrier offsets of the producer / consumer stage
   uint32_t par_c;         // phase parity the consumer waits for
-  int col0;
+  int col0, HD;
 
   __device__ Ring(const Params& p_, uint32_t base_, uint32_t bars_, int h, const CUtensorMap* tq_,
                   const CUtensorMap* td_)
@@ -331,30 +283,16 @@ struct Ring {
     n_it = ((int)blockIdx.x < W) ? (W - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     w_p = blockIdx.x;
     ph_p = 0; c_p = 0;
-    off_p = 0; off_c = (NS - 1) * STAGE;  // off_c is advanced to 0 by the first acquire()
+    off_p = 0; off_c = (NS - 1) * STAGE;         // off_c is advanced to 0 by the first acquire()
     bar_p = 0; bar_c = (NS - 1) * 8; par_c = 1;  // parity flips to 0 when the consumer wraps to slot 0
     HD = p.H * DK;
     col0 = h * DK;
-    gq = nullptr; gd = nullptr; wstep_q = 0; kstep_q = 0; wstep_d = 0; kstep_d = 0;
-    if (!TMA) {
-      cp.init(p.L);
-      const int r0 = threadIdx.x >> 3, c16 = threadIdx.x & 7;
-      gq = p.qkv + ((int64_t)w_p * p.L + r0) * p.ld + h * DK + c16 * 8;
-      wstep_q = (int64_t)gridDim.x * p.L * p.ld;
-      kstep_q = (int64_t)TileCopy<LP>::RSTEP * p.ld;
-      if (BWD) {
-        gd = p.dout + ((int64_t)w_p * p.L + r0) * p.ld_dout + h * DK + c16 * 8;
-        wstep_d = (int64_t)gridDim.x * p.L * p.ld_dout;
-        kstep_d = (int64_t)TileCopy<LP>::RSTEP * p.ld_dout;
-      }
-    } else {
-      if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(bars + s * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-      __syncthreads();
+      for (int s = 0; s < NS; ++s) mbar_init(bars + s * 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
   }
   __device__ __forceinline__ uint32_t cur(int which) const { return base + off_c + which * CT; }
 
@@ -366,63 +304,31 @@ struct Ring {
     if (!single) tma_load_3d(t0 + CT, tb ? td : tq, bar, cb, 0, w_p);
   }
 
-  __device__ __forceinline__ void issue_next() {
+  __device__ __forceinline__ void issue_next() {  // thread 0 only
     if (w_p < (int)p.W) {
-      if (TMA) {
-        const int cq = col0 + c_p * 64;
-        if (!BWD) {
-          if (ph_p == 0) issue_tma(false, 0, cq, 0, cq + HD);
-          else issue_tma(true, 0, cq + 2 * HD, 0, 0);
-        } else {
-          if (ph_p == 0) issue_tma(false, 0, cq, 0, cq + HD);
-          else if (ph_p == 1) issue_tma(false, 1, cq, 0, cq + 2 * HD);
-          else if (ph_p == 2) issue_tma(false, 0, cq + HD, 0, cq);  // K_c, Q_c
-          else issue_tma(true, 1, cq, 0, 0);
-        }
+      const int cq = col0 + c_p * 64;
+      if (!BWD) {
+        if (ph_p == 0) issue_tma(false, 0, cq, 0, cq + HD);  // Q_c, K_c
+        else issue_tma(true, 0, cq + 2 * HD, 0, 0);          // V_c
       } else {
-        const __nv_bfloat16* q = gq + c_p * 64;
-        const uint32_t t0 = base + off_p, t1 = t0 + CT;
-        if (!BWD) {
-          if (ph_p == 0) {
-            cp.load(t0, q, kstep_q, p.qkv);
-            cp.load(t1, q + HD, kstep_q, p.qkv);
-          } else {
-            cp.load(t0, q + 2 * HD, kstep_q, p.qkv);
-          }
-        } else {
-          const __nv_bfloat16* d_o = gd + c_p * 64;
-          if (ph_p == 0) {
-            cp.load(t0, q, kstep_q, p.qkv);
-            cp.load(t1, q + HD, kstep_q, p.qkv);
-          } else if (ph_p == 1) {
-            cp.load(t0, d_o, kstep_d, p.qkv);
-            cp.load(t1, q + 2 * HD, kstep_q, p.qkv);
-          } else if (ph_p == 2) {
-            cp.load(t0, q + HD, kstep_q, p.qkv);  // K_c
-            cp.load(t1, q, kstep_q, p.qkv);       // Q_c
-          } else {
-            cp.load(t0, d_o, kstep_d, p.qkv);
-          }
-        }
+        if (ph_p == 0) issue_tma(false, 0, cq, 0, cq + HD);           // Q_c, K_c
+        else if (ph_p == 1) issue_tma(false, 1, cq, 0, cq + 2 * HD);  // dO_c, V_c
+        else if (ph_p == 2) issue_tma(false, 0, cq + HD, 0, cq);      // K_c, Q_c
+        else issue_tma(true, 1, cq, 0, 0);                            // dO_c
       }
       if (++c_p == NC) {
         c_p = 0;
         if (++ph_p == NPH) {
           ph_p = 0;
           w_p += gridDim.x;
-          if (!TMA) {
-            gq += wstep_q;
-            if (BWD) gd += wstep_d;
-          }
         }
       }
       off_p = (off_p + STAGE == NS * STAGE) ? 0u : off_p + STAGE;
       bar_p = (bar_p + 8 == NS * 8) ? 0u : bar_p + 8;
     }
-    if (!TMA) cp_async_commit();  // always commit (possibly empty) so the group accounting stays uniform
   }
   __device__ __forceinline__ void prologue() {
-    if (!TMA || threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
 #pragma unroll
       for (int i = 0; i < NS - 1; ++i) issue_next();
     }
@@ -430,20 +336,11 @@ struct Ring {
   // Makes the next stage resident and visible to all warps (-> cur()), then refills the slot consumed one step earlier.
   __device__ __forceinline__ void acquire() {
     off_c = (off_c + STAGE == NS * STAGE) ? 0u : off_c + STAGE;
-    if (TMA) {
-      bar_c = (bar_c + 8 == NS * 8) ? 0u : bar_c + 8;
-      if (bar_c == 0) par_c ^= 1u;
-      mbar_wait(bars + bar_c, par_c);
-      __syncthreads();
-      if (threadIdx.x == 0) issue_next();
-    } else {
-      cp_async_wait<NS - 2>();
-      __syncthreads();
-      issue_next();
-    }
-  }
-  __device__ __forceinline__ void drain() {
-    if (!TMA) cp_async_wait<0>();
+    bar_c = (bar_c + 8 == NS * 8) ? 0u : bar_c + 8;
+    if (bar_c == 0) par_c ^= 1u;
+    mbar_wait(bars + bar_c, par_c);
+    __syncthreads();
+    if (threadIdx.x == 0) issue_next();
   }
 };
 
@@ -468,13 +365,13 @@ __device__ __forceinline__ void store_chunk(const float (&acc)[8][4], __nv_bfloa
 // ==========================================================================================
 // Forward
 // ==========================================================================================
-template <int LP, int DK, int NS, bool TMA>
+template <int LP, int DK, int NS>
 __global__ void __launch_bounds__(LP / 16 * 32, LP > 64 ? 3 : 4)
 attn_fwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv) {
   Params p = p_in;
   p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
-  using R = Ring<LP, DK, NS, false, TMA>;
+  using R = Ring<LP, DK, NS, false>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const int h = blockIdx.y;
@@ -530,21 +427,20 @@ attn_fwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv) {
       store_chunk(o, obase + c * 64, p.ld_out, m0, p.L, lane);
     }
   }
-  ring.drain();
   (void)NW;
 }
 
 // ==========================================================================================
 // Backward
 // ==========================================================================================
-template <int LP, int DK, int NS, bool TMA>
+template <int LP, int DK, int NS>
 __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2)
 attn_bwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do) {
   Params p = p_in;
   p.offset += rng_step();
   constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
   constexpr int PP = (LP + 8) * 2;  // padded row pitch (bytes) of the bf16 Pd / dS tiles
-  using R = Ring<LP, DK, NS, true, TMA>;
+  using R = Ring<LP, DK, NS, true>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const int h = blockIdx.y;
@@ -664,8 +560,6 @@ attn_bwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv, c
       }
     }
   }
-  ring.drain();
-
   if (p.dbias != nullptr) {
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
@@ -720,16 +614,7 @@ static int make_tmap3d(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t L
   return LSTC_OK;
 }
 
-static bool use_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LSTC_ATTN_TMA");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-template <int LP, int DK, bool BWD, bool TMA>
+template <int LP, int DK, bool BWD>
 static int launch(const Params& p, cudaStream_t stream) {
   constexpr int NS = 3;
   constexpr int NW = LP / 16;
@@ -744,16 +629,14 @@ static int launch(const Params& p, cudaStream_t stream) {
   CUtensorMap tq, td;
   memset(&tq, 0, sizeof(tq));
   memset(&td, 0, sizeof(td));
-  if (TMA) {
-    int rc = make_tmap3d(&tq, p.qkv, 3 * (int64_t)HD, p.L, p.W, p.ld, LP);
+  int rc = make_tmap3d(&tq, p.qkv, 3 * (int64_t)HD, p.L, p.W, p.ld, LP);
+  if (rc != LSTC_OK) return rc;
+  if (BWD) {
+    rc = make_tmap3d(&td, p.dout, HD, p.L, p.W, p.ld_dout, LP);
     if (rc != LSTC_OK) return rc;
-    if (BWD) {
-      rc = make_tmap3d(&td, p.dout, HD, p.L, p.W, p.ld_dout, LP);
-      if (rc != LSTC_OK) return rc;
-    }
   }
   if (BWD) {
-    auto kern = attn_bwd_kernel<LP, DK, NS, TMA>;
+    auto kern = attn_bwd_kernel<LP, DK, NS>;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -765,7 +648,7 @@ static int launch(const Params& p, cudaStream_t stream) {
     if (gx > p.W) gx = p.W;
     kern<<<dim3((unsigned)gx, (unsigned)p.H), NW * 32, SMEM, stream>>>(p, tq, td);
   } else {
-    auto kern = attn_fwd_kernel<LP, DK, NS, TMA>;
+    auto kern = attn_fwd_kernel<LP, DK, NS>;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       LSTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -784,11 +667,8 @@ static int launch(const Params& p, cudaStream_t stream) {
 template <int DK>
 static int dispatch_lp(bool bwd, const Params& p, cudaStream_t stream) {
   const int L = p.L;
-#define LSTC_ATTN_CASE(LPV)                                                                                   \
-  if (L <= LPV) {                                                                                             \
-    if (use_tma()) return bwd ? launch<LPV, DK, true, true>(p, stream) : launch<LPV, DK, false, true>(p, stream); \
-    return bwd ? launch<LPV, DK, true, false>(p, stream) : launch<LPV, DK, false, false>(p, stream);          \
-  }
+#define LSTC_ATTN_CASE(LPV) \
+  if (L <= LPV) return bwd ? launch<LPV, DK, true>(p, stream) : launch<LPV, DK, false>(p, stream);
   LSTC_ATTN_CASE(16)
   LSTC_ATTN_CASE(32)
   LSTC_ATTN_CASE(48)
