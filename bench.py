@@ -459,8 +459,8 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops_sustained"]) if achieved else None,
                          # mean dram__bytes_read+write per GEMM launch over the 40 launches of one step (ncu capture in
-                         # profiles/r1_step_launches_traffic_v5_2cta.txt; algorithmic operand+result bytes average 0.80 GB)
-                         "traffic": 1.041e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
+                         # profiles/r1_step_launches_traffic_v7_final.txt; algorithmic operand+result bytes average 0.80 GB)
+                         "traffic": 1.114e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
                          "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM launches of the pass)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained", "gemm_share_of_step": gms / ms_prof,
                          "measured": "CUDA-event pair around every GEMM launch during a second timed pass of the same K "
