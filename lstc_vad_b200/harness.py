@@ -441,6 +441,18 @@ def video_windows(n_clips: int, part_len: int, backshift: bool) -> List[Tuple[in
     return out
 
 
+def window_plan(n_clips: int, part_len: int, backshift: bool) -> Tuple[int, Optional[Tuple[int, int, int]]]:
+    """The same windows as `video_windows`, in the form the batched scorer wants: (number of full windows, which are
+    the contiguous clips [0, n_full*part_len) and can be taken as ONE strided view, and the ragged trailing window
+    (feat_beg, feat_end, n_clips_covered) or None)."""
+    n_full, rem = divmod(n_clips, part_len)
+    if rem == 0:
+        return n_full, None
+    if backshift and n_clips >= part_len:
+        return n_full, (n_clips - part_len, n_clips, rem)
+    return n_full, (n_full * part_len, n_clips, rem)
+
+
 def shard_videos(keys: Sequence[str], n_clips: Sequence[int], world: int, rank: int) -> List[int]:
     """Greedy longest-first assignment of videos to ranks (balanced by clip count); returns this rank's indices."""
     order = sorted(range(len(keys)), key=lambda i: (-n_clips[i], keys[i]))
@@ -473,16 +485,13 @@ def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torc
     groups: Dict[int, List[Tuple[str, int, torch.Tensor]]] = {}   # clips per window -> [(key, first window index, [n, c*N, D])]
     for key, feats in videos.items():
         f = feats[:, :n_patch] if n_patch is not None else feats
-        n, D = f.shape[0], f.shape[-1]
-        n_full = n // T
+        D = f.shape[-1]
+        n_full, tail = window_plan(f.shape[0], T, backshift)
         if n_full:
             groups.setdefault(T, []).append((key, 0, f[:n_full * T].reshape(n_full, -1, D)))
-        rem = n - n_full * T
-        if rem:
-            if backshift and n >= T:
-                groups.setdefault(T, []).append((key, n_full, f[n - T:n].reshape(1, -1, D)))
-            else:
-                groups.setdefault(rem, []).append((key, n_full, f[n_full * T:n].reshape(1, -1, D)))
+        if tail is not None:
+            beg, end, _ = tail
+            groups.setdefault(end - beg, []).append((key, n_full, f[beg:end].reshape(1, -1, D)))
     win_scores: Dict[str, Dict[int, torch.Tensor]] = {}
     for _, items in groups.items():
         batch = torch.cat([x for _, _, x in items]).to(dev, non_blocking=True).float()

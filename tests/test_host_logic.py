@@ -137,3 +137,20 @@ def test_weight_cache_is_not_fooled_by_recycled_parameters():
     with torch.no_grad():
         q.add_(1.0)                                                   # optimizer-style in-place update bumps _version
     assert get(q) == 48.0
+
+
+def test_window_plan_is_video_windows_regrouped():
+    """The batched scorer's plan (one view for all full windows + the ragged tail) covers exactly the windows of the
+    reference loops (oracle.window_bounds), for both trailing-window policies."""
+    from lstc_vad_b200.harness import video_windows, window_plan
+    from oracle import lstc_oracle as O
+    for T in (1, 2, 3, 5, 7):
+        for n in range(0, 40):
+            for backshift in (False, True):
+                n_full, tail = window_plan(n, T, backshift)
+                wins = [(i * T, (i + 1) * T) for i in range(n_full)] + ([tail[:2]] if tail else [])
+                if n:
+                    assert wins == O.window_bounds(n, T, backshift=backshift), (n, T, backshift)
+                covers = [T] * n_full + ([tail[2]] if tail else [])
+                assert covers == [c for _, _, c in video_windows(n, T, backshift)], (n, T, backshift)
+                assert sum(covers) == n
