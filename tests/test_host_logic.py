@@ -154,3 +154,28 @@ def test_window_plan_is_video_windows_regrouped():
                 covers = [T] * n_full + ([tail[2]] if tail else [])
                 assert covers == [c for _, _, c in video_windows(n, T, backshift)], (n, T, backshift)
                 assert sum(covers) == n
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one) needs no GPU: one JSON line with
+    the metric / unit of the native arm, `impl`, a `cpu_baseline` describing the run and a zero-copy `e2e`; under
+    torchrun only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "windows/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("windows/sec fwd+bwd") and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                           capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
+    assert other.returncode == 0 and other.stdout.strip() == ""
