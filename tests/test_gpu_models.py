@@ -4,14 +4,16 @@
 
 Stated tolerances.  The CUDA path uses bf16 operands and bf16 activations between kernels with fp32 accumulation /
 statistics.  Calibration: the REFERENCE ITSELF under torch.autocast(bfloat16) vs its own fp32 run moves by
-(oracle/measure_bf16_floor.py, C2 shape) probs max-abs 6.2e-3, x.grad rel-L2 7.7e-2, parameter-gradient rel-L2
-6.9e-2 .. 1.5e-1.  The bounds below are at or inside that floor:
+(oracle/measure_bf16_floor.py) at the C2 shape: probs max-abs 6.2e-3, x.grad rel-L2 7.7e-2, parameter-gradient rel-L2
+6.9e-2 .. 1.5e-1; at the C4 shape (12 windows of 81 tokens, d_model 1024): probs 8.1e-3, x.grad 1.2e-1, parameter
+gradients up to 2.2e-1 (head.classifier.0.bias 2.2e-1, max element error 0.61 x max|ref|).  The bounds below sit at
+that floor:
   scores / probabilities   max-abs <= 1.5e-2, mean-abs <= 4e-3                       (tests/_util.probs_close)
   losses                   abs <= 1e-2
   encoder output / projected values (per tensor): relative Frobenius error <= 6e-2, 99.9 % of the elements
                            within 0.1 * max|ref|, every element within 0.4 * max|ref|  (tests/_util.tensor_close)
   gradients (parameters and input; they cross up to 3 layers of bf16 backward): relative Frobenius error
-                           <= 2e-1 (cosine >= 0.98; the reference's own autocast floor reaches 1.7e-1), 99.9 % within
+                           <= 2.5e-1 (cosine >= 0.97; the reference's own autocast floor reaches 2.2e-1), 99.9 % within
                            0.3 * max|ref|, every element within 1.0 * max|ref| (one ReLU unit flipping on a small
                            batch moves a whole weight row)
   top-k indices / thresholded labels: bit-exact whenever the selected scores are separated by > 3e-2.
@@ -30,7 +32,7 @@ GOLD = Path(__file__).resolve().parent / "golden"
 
 def rel_close(name, got, ref, rel=None, floor=1e-6):
     if "grad" in name:  # gradients have crossed up to 3 layers of bf16 backward: bounded by the autocast floor
-        tensor_close(name, got, ref, rel_l2=2e-1, p999=0.3, max_rel=1.0, floor=floor)
+        tensor_close(name, got, ref, rel_l2=2.5e-1, p999=0.3, max_rel=1.0, floor=floor)
     else:
         tensor_close(name, got, ref, floor=floor)
 
