@@ -179,3 +179,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                            capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_dropin_package_shadows_the_reference_module_paths():
+    """With `dropin/` first on sys.path the reference scripts' own import lines (`from models.Encoder import Encoder`,
+    Train/temporal_transformer_shanghaitech.py:16-18) resolve to the B200 mirror; `utils` is left to the reference."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "from models.Encoder import Encoder\n"
+        "from models.EncoderLayer import EncoderLayer\n"
+        "from models.MultiHeadAttention import MultiHeadAttention, ScaledDotProductAttention\n"
+        "from models.FFN import PositionwiseFeedForward\n"
+        "from models.PatchEmbedding import PatchEmbedding\n"
+        "from models.Classifier import Classifier\n"
+        "from models.Regressor import Regressor\n"
+        "import importlib.util\n"
+        "mods = {c.__module__ for c in (Encoder, EncoderLayer, MultiHeadAttention, PositionwiseFeedForward, PatchEmbedding, Classifier, Regressor)}\n"
+        "assert all(m.startswith('lstc_vad_b200.models.') for m in mods), mods\n"
+        "assert importlib.util.find_spec('utils') is None or 'dropin' not in (importlib.util.find_spec('utils').origin or '')\n"
+        "e = Encoder(n_layers=1, n_head=2, d_k=64, d_v=64, d_model=64, d_inner=128, relative_pe=True, window_size=4, window_depth=3)\n"
+        "assert 'layer_stack.0.slf_attn.relative_position_index' in e.state_dict()\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "dropin") + os.pathsep + root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
