@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP > 64 ? 3 : 4)
 attn_fwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv) {
   Params p = p_in;
   p.offset += rng_step();
-  constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
+  constexpr int NT = LP / 8, KT = LP / 16;
   using R = Ring<LP, DK, NS, false>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -464,7 +464,6 @@ attn_fwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv) {
       store_chunk(o, obase + c * 64, p.ld_out, m0, p.L, lane);
     }
   }
-  (void)NW;
 }
 
 // ==========================================================================================
@@ -475,7 +474,7 @@ __global__ void __launch_bounds__(LP / 16 * 32, LP <= 64 ? 3 : 2)
 attn_bwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do) {
   Params p = p_in;
   p.offset += rng_step();
-  constexpr int NT = LP / 8, KT = LP / 16, NW = LP / 16;
+  constexpr int NT = LP / 8, KT = LP / 16;
   constexpr int PP = (LP + 8) * 2;  // padded row pitch (bytes) of the bf16 Pd / dS tiles
   using R = Ring<LP, DK, NS, true>;
   extern __shared__ __align__(128) uint8_t smem[];

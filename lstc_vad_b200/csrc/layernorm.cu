@@ -10,6 +10,9 @@
 // Both kernels are bound by HBM only if they stay lean: the row statistics of RPI rows are reduced TOGETHER
 // (halving butterfly in the warp, one barrier, a 32-lane second stage), which costs ~1.7 instructions per element
 // instead of the ~10 of per-row shuffle trees plus an all-warps smem read.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "../../include/lstc_vad_b200.h"
 
@@ -495,11 +498,35 @@ static int64_t bwd_grid_max(int64_t rows) {
   if (g < 1) g = 1;
   return g;
 }
+// resident CTAs per SM of (kernel, block size, dynamic smem) on the current device; the function attribute and the
+// occupancy query are issued once per combination and device, not per launch
+struct OccEntry {
+  const void* kern;
+  int threads, dev, occ;
+  size_t smem;
+};
+static int cached_occupancy(const void* kern, int threads, size_t smem) {
+  static std::mutex mu;
+  static std::vector<OccEntry> table;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const OccEntry& e : table)
+    if (e.kern == kern && e.threads == threads && e.smem == smem && e.dev == dev) return e.occ;
+  // the opt-in limit is one attribute per kernel: only ever raise it (the same kernel runs with several block sizes)
+  size_t limit = smem;
+  bool raise = true;
+  for (const OccEntry& e : table)
+    if (e.kern == kern && e.dev == dev && e.smem >= limit) raise = false;
+  if (raise) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  table.push_back(OccEntry{kern, threads, dev, occ, smem});
+  return occ;
+}
 template <typename K>
 static int64_t resident_grid(K kern, int threads, size_t smem, int64_t work, int cap_per_sm) {
-  int occ = 0;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  int occ = cached_occupancy(reinterpret_cast<const void*>(kern), threads, smem);
   if (occ > cap_per_sm) occ = cap_per_sm;
   int64_t g = (int64_t)num_sms() * occ;
   if (g > work) g = work;
