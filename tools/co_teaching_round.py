@@ -8,8 +8,6 @@ import json
 import os
 import sys
 
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")  # train / label phases alternate tensor sizes
-
 import numpy as np
 import torch
 
