@@ -19,7 +19,9 @@ OUT_DIR = PKG_DIR / "_C"
 LIB_PATH = OUT_DIR / "liblstc_vad_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_cls.cu", "layernorm.cu", "elementwise.cu", "heads.cu", "loss.cu"]
+SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_cls.cu", "layernorm.cu", "elementwise.cu", "heads.cu", "loss.cu"]
+
+HEADERS = [CSRC / "common.cuh", CSRC / "ptx_sm100.cuh", CSRC / "attention_params.cuh", INCLUDE / "lstc_vad_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,7 +39,7 @@ def _nvcc() -> str:
 
 
 def _deps() -> list[Path]:
-    return [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", INCLUDE / "lstc_vad_b200.h"]
+    return [CSRC / s for s in SOURCES] + HEADERS
 
 
 def needs_build() -> bool:
@@ -54,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OUT_DIR.mkdir(parents=True, exist_ok=True)
     obj_dir = OUT_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
-    common_t = max((CSRC / "common.cuh").stat().st_mtime, (INCLUDE / "lstc_vad_b200.h").stat().st_mtime)
+    common_t = max(h.stat().st_mtime for h in HEADERS)
 
     def compile_one(src: str) -> Path:
         obj = obj_dir / (src.replace(".cu", ".o"))

@@ -19,7 +19,10 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "attention_params.cuh"
 #include "../../include/lstc_vad_b200.h"
 
 namespace lstc {
@@ -106,23 +109,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
 // index is XOR-swizzled with the row so the 8 rows of one ldmatrix phase hit 8 distinct bank groups
 __device__ __forceinline__ uint32_t ct_off(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
-struct Params {
-  const __nv_bfloat16* qkv;
-  int64_t ld;
-  const __nv_bfloat16* dout;  // bwd
-  int64_t ld_dout;
-  int64_t W;
-  int L, H;
-  const float* bias;  // [H,L,L] or null
-  float scale;
-  float drop_p, drop_scale;
-  uint32_t drop_thr16;
-  uint64_t seed, offset;
-  __nv_bfloat16* out;  // fwd: O ; bwd: dqkv
-  int64_t ld_out;
-  float* probs;  // fwd optional
-  float* dbias;  // bwd optional
-};
 
 // acc (this warp's 16 rows x LP) += A_c[m0.., 0:64] * B_c[:, 0:64]^T, both chunk tiles [rows][64] (k contiguous)
 template <int LP>
@@ -611,43 +597,13 @@ attn_bwd_kernel(const Params p_in, const __grid_constant__ CUtensorMap tm_qkv, c
 }
 
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
 // 3-D bf16 map over [W][L][cols] (row pitch ld elements, window pitch L*ld), box [1][box_rows][64], SWIZZLE_128B,
 // zero fill out of bounds (rows L..box_rows-1 of a window)
 static int make_tmap3d(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t L, int64_t W, int64_t ld, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) {
-    set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver");
-    return LSTC_ERR_DRIVER;
-  }
-  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)W};
-  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * (cuuint64_t)ld * 2};
-  cuuint32_t box[3] = {64u, box_rows, 1u};
-  cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("attention: cuTensorMapEncodeTiled failed (CUresult %d) cols=%lld L=%lld W=%lld ld=%lld", (int)r,
-                   (long long)cols, (long long)L, (long long)W, (long long)ld);
-    return LSTC_ERR_DRIVER;
-  }
-  return LSTC_OK;
+  const uint64_t gdim[3] = {(uint64_t)cols, (uint64_t)L, (uint64_t)W};
+  const uint64_t gstride[2] = {(uint64_t)ld * 2, (uint64_t)L * (uint64_t)ld * 2};
+  const uint32_t box[3] = {64u, box_rows, 1u};
+  return encode_tmap_bf16_sw128(tm, ptr, 3, gdim, gstride, box, 128);
 }
 
 template <int LP, int DK, bool BWD>
@@ -660,7 +616,8 @@ static int launch(const Params& p, cudaStream_t stream) {
   static bool attr_set[64] = {false};
   int dev = 0;
   LSTC_CHECK_CUDA(cudaGetDevice(&dev));
-  static int CTAS_PER_SM = 0;  // resident CTAs per SM for this instantiation (occupancy API: smem + registers)
+  static int ctas_per_sm[64] = {0};  // resident CTAs per SM for this instantiation and device (occupancy API)
+  int& CTAS_PER_SM = ctas_per_sm[(dev >= 0 && dev < 64) ? dev : 0];
   const int HD = p.H * DK;
   CUtensorMap tq, td;
   memset(&tq, 0, sizeof(tq));
@@ -716,7 +673,18 @@ static int dispatch_lp(bool bwd, const Params& p, cudaStream_t stream) {
   return LSTC_ERR_UNSUPPORTED;
 }
 
+// LSTC_ATTN_IMPL=mma selects the mma.sync kernels of this file (kept for A/B measurements); the default is the
+// tcgen05 / TMEM implementation in attention_tc.cu
+static bool use_mma_sync() {
+  static const bool v = [] {
+    const char* e = getenv("LSTC_ATTN_IMPL");
+    return e != nullptr && strcmp(e, "mma") == 0;
+  }();
+  return v;
+}
+
 static int dispatch(bool bwd, const Params& p, int dk, cudaStream_t stream) {
+  if (!use_mma_sync()) return attn_tc::run(bwd, p, dk, stream);
   switch (dk) {
     case 64: return dispatch_lp<64>(bwd, p, stream);
     case 128: return dispatch_lp<128>(bwd, p, stream);

@@ -38,9 +38,17 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();  // SM count of the current device (cached per device)
 
+// Encodes (or fetches from a process-wide cache keyed on every argument) a SWIZZLE_128B bf16 tiled tensor map of rank
+// 2 or 3: gdim[] elements (innermost first), gstride[] BYTES of dims 1.. , box[] elements, zero fill out of bounds.
+// Thread-safe (nn.DataParallel replica threads call the launchers concurrently).  `out` is the driver's 128-byte
+// CUtensorMap.
+int encode_tmap_bf16_sw128(void* out, const void* ptr, int rank, const uint64_t* gdim, const uint64_t* gstride,
+                           const uint32_t* box, int l2_promotion_bytes);
+
 // per translation unit setters of the device-side dropout step pointer (see rng_step() below)
 int set_rng_step_gemm(const void* p);
 int set_rng_step_attention(const void* p);
+int set_rng_step_attention_tc(const void* p);
 int set_rng_step_attention_cls(const void* p);
 int set_rng_step_layernorm(const void* p);
 int set_rng_step_elementwise(const void* p);
