@@ -581,12 +581,12 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
   {
     const uint32_t nbytes = (BWD ? 4u : 2u) * SUB_B;
     for (uint32_t o = threadIdx.x * 16u; o < nbytes; o += NUM_THREADS64 * 16u) st_shared_v4(sP + o, make_uint4(0, 0, 0, 0));
-    if (p.bias != nullptr) {
-      const float* bsrc = p.bias + (int64_t)h * L * L;
-      for (int idx = threadIdx.x; idx < L * L; idx += NUM_THREADS64) {
-        const int r = idx / L;
-        bias_s[r * tp.bias_pitch + (idx - r * L)] = __ldg(bsrc + idx);
-      }
+    // shared-memory bias rows: bias * log2e (0 without a bias) in the columns < L, -inf in the padding columns, so the
+    // softmax needs no column mask
+    const float* bsrc = p.bias != nullptr ? p.bias + (int64_t)h * L * L : nullptr;
+    for (int idx = threadIdx.x; idx < L * LP; idx += NUM_THREADS64) {
+      const int r = idx / LP, c = idx - r * LP;
+      bias_s[r * tp.bias_pitch + c] = c < L ? (bsrc != nullptr ? __ldg(bsrc + r * L + c) * LOG2E : 0.f) : -INFINITY;
     }
   }
   fence_proxy_async();
@@ -607,41 +607,44 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      auto load = [&](const CUtensorMap* tm, int col, int w0) {
+      auto load = [&](const CUtensorMap* tm, int col, int w0, uint64_t policy) {
         mbar_wait(empty_bar(s), ph ^ 1u, 1);
         mbar_arrive_expect_tx(full_bar(s), TILE_B);
-        tma_load_3d(sRing + (uint32_t)s * TILE_B, tm, full_bar(s), col, 0, w0);
+        tma_load_3d_hint(sRing + (uint32_t)s * TILE_B, tm, full_bar(s), col, 0, w0, policy);
         if (++s == NS) { s = 0; ph ^= 1u; }
       };
+      // backward: q, k, dO are read again by the chunk products of the same tile -> keep them in L2 until then;
+      // everything that is read for the last time leaves L2 first
+      const uint64_t pol_again = BWD ? L2_EVICT_LAST : L2_EVICT_FIRST, pol_once = L2_EVICT_FIRST;
       const int cq = h * DK, ck = HD + h * DK, cv = 2 * HD + h * DK;
-      auto load_a = [&](int it) {
+      // load order = the order the MMA warp consumes: A(0), A(1), then per tile and 64-column chunk c the operands of
+      // the chunk products of tile `it` followed by the score operands of tile `it + 2`
+      auto load_a = [&](int it, int c) {
         const int w0 = ((int)blockIdx.x + it * (int)gridDim.x) * G;
-        for (int c = 0; c < NC; ++c) {
-          load(&tm_qkv, cq + 64 * c, w0);
-          load(&tm_qkv, ck + 64 * c, w0);
-        }
-        if (BWD)
-          for (int c = 0; c < NC; ++c) {
-            load(&tm_do, cq + 64 * c, w0);
-            load(&tm_qkv, cv + 64 * c, w0);
-          }
-      };
-      auto load_b = [&](int it) {
-        const int w0 = ((int)blockIdx.x + it * (int)gridDim.x) * G;
-        for (int c = 0; c < NC; ++c) {
-          if (BWD) {
-            load(&tm_qkv, ck + 64 * c, w0);
-            load(&tm_qkv, cq + 64 * c, w0);
-            load(&tm_do, cq + 64 * c, w0);
-          } else {
-            load(&tm_qkv, cv + 64 * c, w0);
-          }
+        load(&tm_qkv, cq + 64 * c, w0, pol_again);
+        load(&tm_qkv, ck + 64 * c, w0, pol_again);
+        if (BWD) {
+          load(&tm_do, cq + 64 * c, w0, pol_again);
+          load(&tm_qkv, cv + 64 * c, w0, pol_once);
         }
       };
-      if (n_my > 0) load_a(0);
+      auto load_b = [&](int it, int c) {
+        const int w0 = ((int)blockIdx.x + it * (int)gridDim.x) * G;
+        if (BWD) {
+          load(&tm_qkv, ck + 64 * c, w0, pol_once);
+          load(&tm_qkv, cq + 64 * c, w0, pol_once);
+          load(&tm_do, cq + 64 * c, w0, pol_once);
+        } else {
+          load(&tm_qkv, cv + 64 * c, w0, pol_once);
+        }
+      };
+      for (int it = 0; it < 2 && it < n_my; ++it)
+        for (int c = 0; c < NC; ++c) load_a(it, c);
       for (int it = 0; it < n_my; ++it) {
-        if (it + 1 < n_my) load_a(it + 1);
-        load_b(it);
+        for (int c = 0; c < NC; ++c) {
+          load_b(it, c);
+          if (it + 2 < n_my) load_a(it + 2, c);
+        }
       }
     }
   } else if (warp == 9) {
@@ -696,17 +699,17 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
         umma_commit(acc_full(slot));
         ++nacc;
       };
-      auto phase_a = [&](int it) {
+      // score products of chunk c of tile `it` (buffer it & 1); the last chunk publishes the buffer to the softmax warps
+      auto phase_a = [&](int it, int c) {
         const uint32_t b = (uint32_t)it & 1u;
-        for (int c = 0; c < NC; ++c) score_product(64u * b, c == 0);
-        if (BWD)
-          for (int c = 0; c < NC; ++c) score_product(DP_COL0 + 64u * b, c == 0);
-        umma_commit(s_full(b));
+        score_product(64u * b, c == 0);
+        if (BWD) score_product(DP_COL0 + 64u * b, c == 0);
+        if (c == NC - 1) umma_commit(s_full(b));
       };
-      if (n_my > 0) phase_a(0);
+      for (int it = 0; it < 2 && it < n_my; ++it)
+        for (int c = 0; c < NC; ++c) phase_a(it, c);
       for (int it = 0; it < n_my; ++it) {
-        if (it + 1 < n_my) phase_a(it + 1);
-        mbar_wait(p_full, (uint32_t)it & 1u, 4);
+        mbar_wait(p_full, (uint32_t)it & 1u, 4);  // also: the softmax has finished reading S / dP buffer it & 1
         tcgen05_fence_after();
         for (int c = 0; c < NC; ++c) {
           if (BWD) {
@@ -716,8 +719,9 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
           } else {
             chunk_product(sP, false);   // O_c = P V_c
           }
+          if (c == NC - 1) umma_commit(p_empty);  // P / dS may be overwritten once these products retire
+          if (it + 2 < n_my) phase_a(it + 2, c);  // HBM-bound score operands interleave with the L2-resident re-reads
         }
-        umma_commit(p_empty);  // P / dS may be overwritten once these products retire
       }
     }
   } else if (warp < 4) {
@@ -732,12 +736,12 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
     const uint32_t cb = (uint32_t)(g2 * LP);  // first column of this row's diagonal block (warp-uniform)
     const uint32_t sPg = sP + (uint32_t)g * SUB_B, sDSg = sDS + (uint32_t)g * SUB_B;
     const float sl2 = p.scale * LOG2E;
-    const bool has_bias = p.bias != nullptr;
     const bool drop = p.drop_p > 0.f;
     const bool want_db = BWD && p.dbias != nullptr;
-    const int ii = i < L ? i : L - 1;
-    const float* brow = bias_s + ii * tp.bias_pitch;
+    const float* brow = bias_s + (i < L ? i : L - 1) * tp.bias_pitch;  // bias * log2e ; -inf in the columns >= L
     const int64_t ld8 = (L + 7) >> 3;
+    const uint32_t thr_hi = p.drop_thr16 << 16;
+    const int c0 = (int)(cb >> 3);            // first 16-byte chunk of the diagonal block in this row of P / dS
     if (want_db) {
       uint32_t z[32];
 #pragma unroll
@@ -754,8 +758,8 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       const int64_t grow = (w * p.H + h) * (int64_t)L + i;
       mbar_wait(s_full(b), ((uint32_t)it >> 1) & 1u, 5);
       tcgen05_fence_after();
-      // ---- the whole score row in registers: v = (s scale + bias) log2e, max, exp2, sum ----
-      float pr[32 * MAXP];
+      // ---- the whole score row in registers: e = exp2((s scale + bias) log2e - max) ; columns >= L come out as 0 ----
+      float e[32 * MAXP];
       float mx = -INFINITY;
 #pragma unroll
       for (int k = 0; k < MAXP; ++k) {
@@ -764,94 +768,93 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int col = 32 * k + j;
-          float x = __uint_as_float(rs[j]) * sl2;
-          if (has_bias && col < L) x = fmaf(brow[col], LOG2E, x);
-          x = col < L ? x : -INFINITY;
-          pr[32 * k + j] = x;
+          const float x = fmaf(__uint_as_float(rs[j]), sl2, brow[32 * k + j]);
+          e[32 * k + j] = x;
           mx = fmaxf(mx, x);
         }
       }
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < 32 * MAXP; ++j) {
-        pr[j] = ex2_approx(pr[j] - mx);
-        sum += pr[j];
+        e[j] = ex2_approx(e[j] - mx);
+        sum += e[j];
       }
-      const float inv = 1.0f / sum;
-      uint32_t keepb[MAXP];
+      // rows of padding (token >= L, window >= W) produce all-zero P / dS rows through this one factor
+      const float inv = valid ? 1.0f / sum : 0.f;
+      const float ic = inv * p.drop_scale;
+      // post-dropout probabilities as packed bf16 (the operand of P V / P^T dO); backward: t = P_dropped * dP
+      uint32_t pk[16 * MAXP];
+      float tt[BWD ? 32 * MAXP : 1];
+      float delta = 0.f;
 #pragma unroll
       for (int k = 0; k < MAXP; ++k) {
-        uint32_t kb = 0xffffffffu;
-        if (drop) {
-          kb = 0u;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int n = 4 * k + u;
-            uint32_t m8 = 0xffu;
-            if (valid && n * 8 < L) m8 = dropout_keep8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), p.drop_thr16);
-            kb |= m8 << (8 * u);
-          }
+        uint32_t rd[32];
+        if (BWD) {
+          tmem_ld_32x32b_x32(trow + DP_COL0 + 64u * b + cb + 32u * k, rd);
+          tmem_ld_wait();
         }
-        keepb[k] = kb;
-      }
-      if (!BWD) {
-        if (it > 0) mbar_wait(p_empty, ((uint32_t)it - 1u) & 1u, 7);  // P V of the previous tile has read P
 #pragma unroll
-        for (int k = 0; k < MAXP; ++k) {
-          float pd[32];
+        for (int u = 0; u < 4; ++u) {
+          const int n = 4 * k + u;
+          uint32_t rnd[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+          if (drop && n * 8 < L) dropout_rand8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), rnd);
+          float pd[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            pd[j] = (valid && ((keepb[k] >> j) & 1u)) ? pr[32 * k + j] * inv * p.drop_scale : 0.f;
-          if (p.probs != nullptr && valid) {
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint32_t word = rnd[jj >> 1];
+            const bool kept = (jj & 1) ? (word >= thr_hi) : ((word << 16) >= thr_hi);
+            pd[jj] = kept ? e[32 * k + 8 * u + jj] * ic : 0.f;
+            if (BWD) {
+              const float x = pd[jj] * __uint_as_float(rd[8 * u + jj]);
+              tt[BWD ? 32 * k + 8 * u + jj : 0] = x;
+              delta += x;
+            }
+          }
+          if (!BWD && p.probs != nullptr && valid) {
             float* prow = p.probs + grow * (int64_t)L;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (32 * k + j < L) prow[32 * k + j] = pd[j];
+            for (int jj = 0; jj < 8; ++jj)
+              if (8 * n + jj < L) prow[8 * n + jj] = pd[jj];
           }
-          store_piece_bf16(sPg, m, (int)cb + 32 * k, pd);
-        }
-      } else {
-        // ---- delta = sum_j p_j dP_j (dP masked by the dropout keep bits) ----
 #pragma unroll
-        for (int j = 0; j < 32 * MAXP; ++j) pr[j] *= inv;
-        float delta = 0.f;
+          for (int jj = 0; jj < 4; ++jj) pk[16 * k + 4 * u + jj] = pack_bf16x2(pd[2 * jj], pd[2 * jj + 1]);
+        }
+      }
+      // ---- backward: scale * dS = scale (t - p delta) as packed bf16 ; bias gradient (kept scaled, unscaled at the
+      // flush).  Everything is computed BEFORE waiting for the previous tile's products to release P / dS, so that only
+      // the 16-byte stores remain on the MMA warp's critical path ----
+      uint32_t dk[BWD ? 16 * MAXP : 1];
+      if (BWD) {
+        const float nk = -inv * delta * p.scale;
 #pragma unroll
         for (int k = 0; k < MAXP; ++k) {
-          uint32_t rd[32];
-          tmem_ld_32x32b_x32(trow + DP_COL0 + 64u * b + cb + 32u * k, rd);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = (((keepb[k] >> j) & 1u) && (32 * k + j < L)) ? __uint_as_float(rd[j]) * p.drop_scale : 0.f;
-            delta = fmaf(pr[32 * k + j], d, delta);
+          uint32_t rb[32];
+          if (want_db) {
+            tmem_ld_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
+            tmem_ld_wait();
           }
-        }
-        if (it > 0) mbar_wait(p_empty, ((uint32_t)it - 1u) & 1u, 7);  // dQ / dK / dV of the previous tile have read P, dS
-        // ---- dS = p (dP - delta) ; bias gradient ; bf16 operands ----
 #pragma unroll
-        for (int k = 0; k < MAXP; ++k) {
-          uint32_t rd[32], rb[32];
-          tmem_ld_32x32b_x32(trow + DP_COL0 + 64u * b + cb + 32u * k, rd);
-          if (want_db) tmem_ld_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
-          tmem_ld_wait();
-          float pd[32], ds[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = 32 * k + j;
-            const bool kept = (keepb[k] >> j) & 1u;
-            const float d = (kept && col < L) ? __uint_as_float(rd[j]) * p.drop_scale : 0.f;
-            float x = pr[32 * k + j] * (d - delta);
-            x = valid ? x : 0.f;  // columns >= L have p = 0
-            if (want_db) rb[j] = __float_as_uint(__uint_as_float(rb[j]) + x);
-            ds[j] = x * p.scale;  // the 1/sqrt(dk) of dQ = scale dS K and dK = scale dS^T Q
-            pd[j] = (valid && kept) ? pr[32 * k + j] * p.drop_scale : 0.f;
+          for (int j2 = 0; j2 < 16; ++j2) {
+            const int j = 32 * k + 2 * j2;
+            const float d0 = fmaf(e[j], nk, tt[BWD ? j : 0] * p.scale);
+            const float d1 = fmaf(e[j + 1], nk, tt[BWD ? j + 1 : 0] * p.scale);
+            if (want_db) {
+              rb[2 * j2] = __float_as_uint(__uint_as_float(rb[2 * j2]) + d0);
+              rb[2 * j2 + 1] = __float_as_uint(__uint_as_float(rb[2 * j2 + 1]) + d1);
+            }
+            dk[BWD ? 16 * k + j2 : 0] = pack_bf16x2(d0, d1);
           }
           if (want_db) tmem_st_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
-          store_piece_bf16(sPg, m, (int)cb + 32 * k, pd);
-          store_piece_bf16(sDSg, m, (int)cb + 32 * k, ds);
         }
         if (want_db) tmem_st_wait();
+      }
+      if (it > 0) mbar_wait(p_empty, ((uint32_t)it - 1u) & 1u, 7);  // the products of the previous tile have read P (dS)
+#pragma unroll
+      for (int c = 0; c < 4 * MAXP; ++c) {
+        st_shared_v4(sPg + sw128(m, c0 + c), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+        if (BWD)
+          st_shared_v4(sDSg + sw128(m, c0 + c), make_uint4(dk[BWD ? 4 * c : 0], dk[BWD ? 4 * c + 1 : 0],
+                                                           dk[BWD ? 4 * c + 2 : 0], dk[BWD ? 4 * c + 3 : 0]));
       }
       fence_proxy_async();
       tcgen05_fence_before();
@@ -859,6 +862,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       if (lane == 0) mbar_arrive(p_full);
     }
     if (want_db) {
+      const float unscale = 1.0f / p.scale;
 #pragma unroll
       for (int k = 0; k < MAXP; ++k) {
         uint32_t rb[32];
@@ -869,7 +873,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = 32 * k + j;
-            if (col >= 1 && col < L) atomicAdd(drow + col, __uint_as_float(rb[j]));
+            if (col >= 1 && col < L) atomicAdd(drow + col, __uint_as_float(rb[j]) * unscale);
           }
         }
       }
@@ -922,7 +926,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
         if (leader) {
           const int c = BWD ? prod / 3 : prod;
           const int which = BWD ? prod - 3 * c : 0;
-          tma_store_3d(&tm_out, stg, which * HD + h * DK + 64 * c, 0, w0);
+          tma_store_3d_hint(&tm_out, stg, which * HD + h * DK + 64 * c, 0, w0, L2_EVICT_FIRST);
           tma_commit_group();
         }
       }
@@ -965,12 +969,24 @@ static int launch(const Params& p, cudaStream_t stream) {
   tp.nkeys = (G > 1) ? 128 : ((p.L + 15) / 16) * 16;
   tp.ks_tok = (G > 1) ? 8 : tp.nkeys / 16;
   tp.npiece = (G > 1) ? LP / 32 : (tp.nkeys + 31) / 32;
-  tp.bias_pitch = p.L | 1;
-  tp.bias_bytes = p.bias != nullptr ? (uint32_t)(((size_t)p.L * tp.bias_pitch * 4 + 15) / 16 * 16) : 0u;
+  if (G > 1) {  // sub-tile kernel: always staged, LP columns per row (padding columns hold -inf)
+    tp.bias_pitch = LP + 1;
+    tp.bias_bytes = (uint32_t)(((size_t)p.L * tp.bias_pitch * 4 + 15) / 16 * 16);
+  } else {
+    tp.bias_pitch = p.L | 1;
+    tp.bias_bytes = p.bias != nullptr ? (uint32_t)(((size_t)p.L * tp.bias_pitch * 4 + 15) / 16 * 16) : 0u;
+  }
   constexpr uint32_t OPERAND_B = (G > 1) ? 8192u : PANEL_B;  // P (and dS): 2 x [64 x 64] or 2 panels of [128 x 64]
   const uint32_t fixed = 1024u + (BWD ? 4u : 2u) * OPERAND_B + 2u * TILE_B + tp.bias_bytes + BAR_BYTES;
   int ns = (int)((SMEM_LIMIT - fixed) / TILE_B);
   if (ns > MAX_STAGES) ns = MAX_STAGES;
+  {
+    static const int cap = [] {  // LSTC_ATTN_STAGES=<n>: cap the ring depth (experiments on latency hiding)
+      const char* e = getenv("LSTC_ATTN_STAGES");
+      return e != nullptr ? atoi(e) : 0;
+    }();
+    if (cap >= 3 && ns > cap) ns = cap;
+  }
   if (ns < 3) {
     set_last_error("attention: no shared memory left for the operand ring (L=%d)", p.L);
     return LSTC_ERR_UNSUPPORTED;

@@ -66,6 +66,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 eviction-priority policies for the .L2::cache_hint forms (the encodings createpolicy.fractional.L2::evict_* yields
+// for fraction 1.0; same constants as cute::TMA::CacheHintSm90)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int32_t c0,
+                                                 int32_t c1, int32_t c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
+      "%5}], [%2], %6;" ::"r"(smem_dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* tmap, uint32_t smem_src, int32_t c0, int32_t c1,
+                                                  int32_t c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                   tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+               : "memory");
+}
 // shared -> global tile store; elements outside the tensor's extents are not written
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, uint32_t smem_src, int32_t c0, int32_t c1,
                                              int32_t c2) {
