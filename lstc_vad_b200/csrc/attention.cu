@@ -673,18 +673,24 @@ static int dispatch_lp(bool bwd, const Params& p, cudaStream_t stream) {
   return LSTC_ERR_UNSUPPORTED;
 }
 
-// LSTC_ATTN_IMPL=mma selects the mma.sync kernels of this file (kept for A/B measurements); the default is the
-// tcgen05 / TMEM implementation in attention_tc.cu
-static bool use_mma_sync() {
-  static const bool v = [] {
+// Implementation choice.  Default: the tcgen05 / TMEM kernels of attention_tc.cu for windows of up to 64 tokens (their
+// software-pipelined sub-tile kernel), the mma.sync kernels of this file for 65..96 tokens (measured on B200 at L = 81:
+// 0.55 / 1.50 ms against 0.58 / 1.59 ms of the single-buffered M = 128 tcgen05 kernel).  LSTC_ATTN_IMPL=mma | tc forces one
+// implementation for every length (A/B measurements).
+static int attn_impl_override() {
+  static const int v = [] {
     const char* e = getenv("LSTC_ATTN_IMPL");
-    return e != nullptr && strcmp(e, "mma") == 0;
+    if (e == nullptr) return 0;
+    if (strcmp(e, "mma") == 0) return 1;
+    if (strcmp(e, "tc") == 0) return 2;
+    return 0;
   }();
   return v;
 }
 
 static int dispatch(bool bwd, const Params& p, int dk, cudaStream_t stream) {
-  if (!use_mma_sync()) return attn_tc::run(bwd, p, dk, stream);
+  const int force = attn_impl_override();
+  if (force == 2 || (force == 0 && p.L <= 64)) return attn_tc::run(bwd, p, dk, stream);
   switch (dk) {
     case 64: return dispatch_lp<64>(bwd, p, stream);
     case 128: return dispatch_lp<128>(bwd, p, stream);
