@@ -229,6 +229,22 @@ int lstc_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream
 int lstc_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, float lr, float weight_decay,
                       float eps, float grad_scale, const float* grad_scale_dev, void* stream);
 
+/* ---- multi-tensor launches: ONE kernel per call walks a table of up to 48 tensors (longer tables are split); the
+ * pointer / size tables are HOST arrays (copied into the kernel parameters), every tensor pointer is a device pointer.
+ *
+ * lstc_multi_pack_bf16 / lstc_multi_unpack_bf16: the fp32 gradients of one data-parallel bucket <-> one flat bf16
+ * buffer, the payload of the NCCL all-reduce that replaces nn.DataParallel's reduce_add_coalesced
+ * (Train/temporal_transformer_shanghaitech.py:76-78).  dst / src pointers of the flat side are (flat + offset), 16-byte
+ * aligned.
+ * lstc_multi_adagrad: lstc_adagrad_step for every parameter in one launch; lrs[i] per tensor (the scripts use two
+ * parameter groups, :83-85); grads are fp32 tensors or (grad_is_bf16 != 0) slices of a reduced bf16 bucket. */
+int lstc_multi_pack_bf16(const void* const* src_f32, const int64_t* numel, int n, void* const* dst_bf16, void* stream);
+int lstc_multi_unpack_bf16(const void* const* src_bf16, const int64_t* numel, int n, void* const* dst_f32,
+                           void* stream);
+int lstc_multi_adagrad(void* const* params, const void* const* grads, int grad_is_bf16, void* const* states,
+                       const int64_t* numel, const float* lrs, int n, float weight_decay, float eps, float grad_scale,
+                       const float* grad_scale_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

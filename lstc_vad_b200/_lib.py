@@ -56,6 +56,9 @@ SIGNATURES: dict[str, tuple] = {
     "lstc_sumsq_accumulate": (_I, [_P, _L, _P, _P]),
     "lstc_clip_coef": (_I, [_P, _F, _P, _P]),
     "lstc_adagrad_step": (_I, [_P, _P, _P, _L, _F, _F, _F, _F, _P, _P]),
+    "lstc_multi_pack_bf16": (_I, [_P, _P, _I, _P, _P]),
+    "lstc_multi_unpack_bf16": (_I, [_P, _P, _I, _P, _P]),
+    "lstc_multi_adagrad": (_I, [_P, _P, _I, _P, _P, _P, _I, _F, _F, _F, _P, _P]),
 }
 
 _lib = None

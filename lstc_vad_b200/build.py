@@ -19,7 +19,7 @@ OUT_DIR = PKG_DIR / "_C"
 LIB_PATH = OUT_DIR / "liblstc_vad_b200.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_cls.cu", "layernorm.cu", "elementwise.cu", "heads.cu", "loss.cu"]
+SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_cls.cu", "layernorm.cu", "elementwise.cu", "multitensor.cu", "heads.cu", "loss.cu"]
 
 HEADERS = [CSRC / "common.cuh", CSRC / "ptx_sm100.cuh", CSRC / "attention_params.cuh", INCLUDE / "lstc_vad_b200.h"]
 

@@ -31,6 +31,30 @@ _rng_lock = threading.Lock()
 _rng_state = {"seed": None, "offset": 0}
 
 
+_rng_counters = {}  # device index -> int64[1] tensor registered with the library (lives for the whole process)
+
+
+def device_rng_counter(device=None) -> torch.Tensor:
+    """The device-resident dropout step counter of `device`, shared by every CUDA graph of the process.
+
+    Every mask-drawing kernel adds its value to the `offset` argument it was launched with, so a replayed graph (which
+    bakes seed / offset by value) draws fresh masks as long as the graph bumps the counter.  ONE counter per device is
+    allocated on first use, registered with `lstc_set_rng_step` and never freed or re-pointed: the registration is a
+    per-device __constant__ pointer inside the library, so per-graph counters would silently re-point each other's
+    kernels (and a freed one would dangle)."""
+    from . import _lib
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _rng_lock:
+        t = _rng_counters.get(idx)
+        if t is None:
+            with torch.cuda.device(idx):
+                t = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+                _lib.check(_lib.load().lstc_set_rng_step(t.data_ptr()), "lstc_set_rng_step")
+            _rng_counters[idx] = t
+        return t
+
+
 def set_dropout_stream(seed: int, offset: int = 0) -> None:
     """Pins the dropout stream (e.g. seed + rank for data-parallel replicas)."""
     with _rng_lock:

@@ -115,7 +115,8 @@ class TrainStep:
     def __init__(self, wl: Workload, device: torch.device, seed: int = 0, train_mode: bool = True,
                  lambda_1: float = 0.01, lambda_MIL: float = 1.0, lambda_CE: float = 0.8,
                  process_group=None, optimizer: bool = False, lr_encoder: float = 1e-4, lr_head: float = 1e-2,
-                 weight_decay: float = 1e-3, clip_grad_norm: Optional[float] = None, cls_fast_path: bool = False):
+                 weight_decay: float = 1e-3, clip_grad_norm: Optional[float] = None, cls_fast_path: bool = False,
+                 dp_grad_dtype: Optional[str] = None):
         self.wl, self.device = wl, device
         self.lambda_1, self.lambda_MIL, self.lambda_CE = lambda_1, lambda_MIL, lambda_CE
         self.cls_fast_path = cls_fast_path  # Encoder.forward_cls: skips the last layer's dead (non-CLS) work
@@ -134,7 +135,7 @@ class TrainStep:
         Fn.set_dropout_stream(seed * 1000003 + 7919 * self.rank + 1)
         self.reducer = None
         if self.world > 1:
-            self.reducer = BucketedGradReducer([self.encoder, self.head], process_group)
+            self.reducer = BucketedGradReducer([self.encoder, self.head], process_group, grad_dtype=dp_grad_dtype)
         self.opt = None
         if optimizer:
             self.opt = FusedAdagrad([(list(self.encoder.parameters()), lr_encoder),
@@ -233,7 +234,6 @@ class GraphedTrainStep:
 
     def __init__(self, step: "TrainStep", feats: torch.Tensor, labs: Optional[torch.Tensor], local_batch: int,
                  warmup: int = 3):
-        from . import _lib
         # Autograd's AccumulateGrad nodes remember the stream of the forward that created them and live as long as any
         # autograd graph of an earlier (eager, default-stream) step is referenced; such a node would make the legacy
         # stream wait on the capturing stream.  Drop dead graphs so the side-stream warm-up below re-creates the nodes.
@@ -244,9 +244,8 @@ class GraphedTrainStep:
         self.step, self.local_batch = step, local_batch
         self.static_feats = feats.clone()
         self.static_labs = labs.clone() if labs is not None else None
-        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=feats.device)
-        self._lib = _lib.load()
-        _lib.check(self._lib.lstc_set_rng_step(self.rng_counter.data_ptr()), "lstc_set_rng_step")
+        # process-wide per-device counter (shared by all graphs; see functional.device_rng_counter)
+        self.rng_counter = Fn.device_rng_counter(feats.device)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -274,8 +273,10 @@ class GraphedTrainStep:
         return self.terms
 
     def close(self):
-        from . import _lib
-        _lib.check(self._lib.lstc_set_rng_step(None), "lstc_set_rng_step")
+        """Releases the captured graph (its collectives, static buffers and autograd state).  The dropout step counter
+        is shared by every graph of the process and stays registered."""
+        self.graph = None
+        self.terms = None
 
 
 class _InjectGrad(torch.autograd.Function):
@@ -301,12 +302,19 @@ class BucketedGradReducer:
     soon as the last gradient of the bucket has been accumulated.  The bucket plan is static and only contains parameters
     that receive gradients (LayerNorms switched off by the model flags never do — SURVEY.md §8)."""
 
-    def __init__(self, modules: Sequence[torch.nn.Module], process_group, comm_stream: Optional[torch.cuda.Stream] = None):
+    def __init__(self, modules: Sequence[torch.nn.Module], process_group, comm_stream: Optional[torch.cuda.Stream] = None,
+                 grad_dtype: Optional[str] = None):
         import torch.distributed as dist
         self.dist, self.pg = dist, process_group
         self.buckets: List[List[torch.nn.Parameter]] = []
         self._plan(modules)
-        self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self.flat: List[Optional[tuple]] = [None] * len(self.buckets)  # (param ids, flat buffer, offsets)
+        # payload dtype of the gradient all-reduce: "bf16" (default; fp32 gradients are rounded once before the sum,
+        # relative error ~2^-9 per element, well inside the bf16 activation noise of the step) or "fp32" (exact sum,
+        # as nn.DataParallel's reduce_add_coalesced)
+        self.grad_dtype = grad_dtype or os.environ.get("LSTC_DP_GRAD_DTYPE", "bf16")
+        if self.grad_dtype not in ("bf16", "fp32"):
+            raise ValueError(f"LSTC_DP_GRAD_DTYPE must be bf16 or fp32, got {self.grad_dtype!r}")
         self.pending: List[int] = [0] * len(self.buckets)
         self.handles = []
         self.stream = comm_stream or torch.cuda.Stream()
@@ -364,26 +372,47 @@ class BucketedGradReducer:
         for bi, bucket in enumerate(self.buckets):
             self.pending[bi] = sum(1 for p in bucket if id(p) not in self._skip)
 
+    ALIGN = 64  # elements: every tensor starts on a 128-byte (bf16) / 256-byte (fp32) boundary of its flat bucket
+
+    def _layout(self, bi, ps):
+        """(flat buffer, per-tensor offsets) of bucket `bi` for the parameter list `ps` (static after the first steps)."""
+        key = tuple(id(p) for p in ps)
+        cached = self.flat[bi]
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        offsets, off = [], 0
+        for p in ps:
+            offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        dtype = torch.bfloat16 if self.grad_dtype == "bf16" else torch.float32
+        flat = torch.zeros(off, device=ps[0].device, dtype=dtype)  # zeros: the alignment gaps travel through the reduce
+        self.flat[bi] = (key, flat, offsets)
+        return flat, offsets
+
     def _launch(self, bi):
         ps = [p for p in self.buckets[bi] if id(p) not in self._skip and p.grad is not None]
         if not ps:
             return
-        n = sum(p.numel() for p in ps)
-        if self.flat[bi] is None or self.flat[bi].numel() != n:
-            self.flat[bi] = torch.empty(n, device=ps[0].device, dtype=torch.float32)
-        flat = self.flat[bi]
-        views, off = [], 0
-        for p in ps:
-            views.append(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        torch._foreach_copy_(views, [p.grad for p in ps])
+        flat, offsets = self._layout(bi, ps)
+        grads = [p.grad for p in ps]
+        views = None
+        if self.grad_dtype == "bf16":
+            # one launch: fp32 gradients -> the flat bf16 all-reduce payload (half the NVLink bytes of an fp32 bucket)
+            ops.multi_pack_bf16(grads, flat, offsets)
+        else:
+            views = [flat[o:o + p.numel()].view_as(p) for o, p in zip(offsets, ps)]
+            torch._foreach_copy_(views, grads)
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
             self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.pg)
-        for p, v in zip(ps, views):
-            p.grad = v  # the optimizer reads the reduced bucket in place
+            # the reduced gradient goes back into the parameters' own .grad tensors (in place, on the side stream, so
+            # it overlaps the rest of backward as well): no tensor is re-bound, the optimizer sees ordinary fp32 grads
+            if self.grad_dtype == "bf16":
+                ops.multi_unpack_bf16(flat, offsets, grads)
+            else:
+                torch._foreach_copy_(grads, views)
         self.handles.append(bi)
 
     def finish(self):
@@ -401,8 +430,10 @@ class BucketedGradReducer:
 
 
 class FusedAdagrad:
-    """torch.optim.Adagrad(lr per group, weight_decay) semantics (Train/temporal_transformer_shanghaitech.py:83-85)
-    with one fused kernel per parameter: 5 HBM passes (read grad/param/state, write param/state)."""
+    """torch.optim.Adagrad(lr per group, weight_decay) semantics (Train/temporal_transformer_shanghaitech.py:83-85) as
+    ONE multi-tensor launch over every parameter that has a gradient (5 HBM passes: read grad / param / state, write
+    param / state); with `clip_grad_norm` one launch per parameter group, each consuming its own device-side clip
+    coefficient (the scripts clip per model, :139-141)."""
 
     def __init__(self, groups, weight_decay: float, eps: float = 1e-10, clip_grad_norm: Optional[float] = None):
         self.groups = groups
@@ -410,15 +441,30 @@ class FusedAdagrad:
         self.clip = clip_grad_norm  # per group, like the scripts' per-model clip_grad_norm_(.., 10)
         self.state: Dict[int, torch.Tensor] = {}
 
+    def _state(self, p):
+        st = self.state.get(id(p))
+        if st is None:
+            st = self.state[id(p)] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return st
+
     def step(self):
+        ps, gs, sts, lrs = [], [], [], []
         for params, lr in self.groups:
             live = [p for p in params if p.grad is not None]
-            coef = ops.grad_clip_coef([p.grad for p in live], self.clip) if (self.clip and live) else None
-            for p in live:
-                st = self.state.get(id(p))
-                if st is None:
-                    st = self.state[id(p)] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                ops.adagrad_step(p.data, p.grad.contiguous(), st, lr, self.wd, self.eps, 1.0, coef)
+            if not live:
+                continue
+            grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in live]
+            states = [self._state(p) for p in live]
+            if self.clip:
+                coef = ops.grad_clip_coef(grads, self.clip)
+                ops.multi_adagrad([p.data for p in live], grads, states, [lr] * len(live), self.wd, self.eps, 1.0, coef)
+            else:
+                ps += [p.data for p in live]
+                gs += grads
+                sts += states
+                lrs += [lr] * len(live)
+        if ps:
+            ops.multi_adagrad(ps, gs, sts, lrs, self.wd, self.eps)
         Fn.invalidate_weight_cache()  # parameters were updated through raw pointers
 
 
@@ -493,16 +539,35 @@ def score_videos(encoder: Encoder, head: torch.nn.Module, videos: Dict[str, torc
             beg, end, _ = tail
             groups.setdefault(end - beg, []).append((key, n_full, f[beg:end].reshape(1, -1, D)))
     win_scores: Dict[str, Dict[int, torch.Tensor]] = {}
+    def run(xin):
+        sc = head(encoder.forward_cls(xin) if cls_fast_path else encoder(xin)[:, 0, :])
+        sc = sc[:, 1] if is_cls else sc[:, 0]
+        if threshold is not None:
+            sc = losses.threshold_pseudo_labels(sc, threshold)
+        return sc.float()
+
     for _, items in groups.items():
-        batch = torch.cat([x for _, _, x in items]).to(dev, non_blocking=True).float()
-        outs = []
-        for s0 in range(0, batch.shape[0], max_windows):
-            xin = batch[s0:s0 + max_windows]
-            sc = head(encoder.forward_cls(xin) if cls_fast_path else encoder(xin)[:, 0, :])
-            sc = sc[:, 1] if is_cls else sc[:, 0]
-            if threshold is not None:
-                sc = losses.threshold_pseudo_labels(sc, threshold)
-            outs.append(sc.float())
+        # forward calls of up to `max_windows` windows, assembled from consecutive videos: the concatenated copy of the
+        # inputs never exceeds one call's worth (a corpus-sized torch.cat would double the resident features)
+        outs, pending, n_pending = [], [], 0
+
+        def flush():
+            nonlocal pending, n_pending
+            if pending:
+                xin = (pending[0] if len(pending) == 1 else torch.cat(pending)).to(dev, non_blocking=True).float()
+                outs.append(run(xin))
+                pending, n_pending = [], 0
+
+        for _, _, x in items:
+            s0 = 0
+            while s0 < x.shape[0]:
+                take = min(x.shape[0] - s0, max_windows - n_pending)
+                pending.append(x[s0:s0 + take])
+                n_pending += take
+                s0 += take
+                if n_pending == max_windows:
+                    flush()
+        flush()
         sc = torch.cat(outs).cpu()
         off = 0
         for key, w0, x in items:
@@ -567,6 +632,10 @@ def sample_window_indices(feat_len: int, part_num: int, part_len: int, sample: s
     `np.random` / RandomState reproduces the reference's choice.  Returns int64 [part_num * part_len]."""
     import numpy as np
     rng = rng if rng is not None else np.random
+    if feat_len < part_len:
+        # the reference's numpy fancy-indexing raises (or silently wraps negative indices) here; a device gather would
+        # read out of bounds instead, so refuse up front
+        raise IndexError(f"sample_window_indices: video of {feat_len} clips is shorter than part_len {part_len}")
     base = np.linspace(0, feat_len - part_len, num=part_num + 1, dtype=int)
     if sample == "uniform":
         span = (feat_len - part_len) // (part_num + 1)
@@ -581,7 +650,11 @@ def sample_window_indices(feat_len: int, part_num: int, part_len: int, sample: s
         else:
             move = rng.randint(0, gap, [part_num + 1]).repeat(part_len).reshape([-1, part_len])
         chosen = chosen + move
-    return chosen.reshape([-1])[: part_num * part_len].astype("int64")
+    chosen = chosen.reshape([-1])[: part_num * part_len].astype("int64")
+    if chosen.min() < 0 or chosen.max() >= feat_len:
+        raise IndexError(f"sample_window_indices: clip index out of range [0, {feat_len}) "
+                         f"(min {chosen.min()}, max {chosen.max()})")
+    return chosen
 
 
 class DeviceCorpus:
@@ -642,6 +715,72 @@ def synthetic_corpus(n_videos: int, n_patch: int, d_model: int, device, seed: in
         f = torch.randn(n, n_patch, d_model, device=device, generator=g).abs_()
         (abnormal if i % 2 else normal)[f"v{i:05d}"] = f
     return normal, abnormal
+
+
+def synthetic_video_lengths(n_videos: int, seed: int = 0, mean_clips: float = 50.0, min_clips: int = 24,
+                            max_clips: int = 160) -> List[int]:
+    """Clip counts of the synthetic corpus of SURVEY.md §8d (config C5): log-normal around `mean_clips`.  Host-only, so
+    every rank can plan the sharding of the whole corpus without generating it."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    return [int(np.clip(rs.lognormal(np.log(mean_clips), 0.5), min_clips, max_clips)) for _ in range(n_videos)]
+
+
+def synthetic_video(index: int, n_clips: int, n_patch: int, d_model: int, device, seed: int = 0) -> torch.Tensor:
+    """Features of video `index` of the synthetic corpus, fp32 [n_clips, n_patch, d_model], generated in HBM from a
+    per-video seed: the same tensor whatever rank (and however many ranks) generates it."""
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + 7 * index + 1)
+    return torch.randn(n_clips, n_patch, d_model, device=device, generator=g).abs_()
+
+
+def sharded_label_sweep(encoder: Encoder, head: torch.nn.Module, n_videos: int, part_len: int, n_patch: int,
+                        world: int = 1, rank: int = 0, threshold: Optional[float] = 0.65, seed: int = 0,
+                        backshift: bool = False, cls_fast_path: bool = False, max_windows: int = 4096,
+                        only_abnormal: bool = False, videos: Optional[Dict[str, torch.Tensor]] = None):
+    """This rank's share of the pseudo-label generation sweep over the synthetic corpus (the loop of
+    Train/pseudo_labels_generator_temporal.py:113-143 over every training video, batched and sharded by video with NO
+    collective): the corpus is planned on the host (`synthetic_video_lengths`), assigned with `shard_videos` (greedy,
+    balanced by clip count) and only this rank's videos are generated and scored.
+    Returns (scores {key: fp32 [n_clips]}, stats dict with the device seconds of the sweep and its window count)."""
+    d_model = encoder.layer_norm.weight.shape[0]
+    dev = next(encoder.parameters()).device
+    lengths = synthetic_video_lengths(n_videos, seed)
+    keys = [f"v{i:05d}" for i in range(n_videos)]
+    ids = [i for i in range(n_videos) if (i % 2 == 1 or not only_abnormal)]
+    mine = shard_videos([keys[i] for i in ids], [lengths[i] for i in ids], world, rank)
+    if videos is None:
+        videos = {keys[ids[j]]: synthetic_video(ids[j], lengths[ids[j]], n_patch, d_model, dev, seed) for j in mine}
+    n_windows = sum(-(-int(v.shape[0]) // part_len) for v in videos.values())
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    scores = score_videos(encoder, head, videos, part_len=part_len, threshold=threshold, n_patch=n_patch,
+                          backshift=backshift, cls_fast_path=cls_fast_path, max_windows=max_windows)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return scores, dict(seconds=e0.elapsed_time(e1) * 1e-3, windows=n_windows, videos=len(videos),
+                        clips=sum(int(v.shape[0]) for v in videos.values()))
+
+
+def merge_label_dicts(local: Dict[str, torch.Tensor], process_group=None) -> Optional[Dict[str, torch.Tensor]]:
+    """Rank 0 receives every rank's {key: scores} dict and returns their union in key order (the other ranks return
+    None) - the only exchange of the sharded sweep, after the timed region
+    (Train/pseudo_labels_generator_temporal.py:145 then saves ONE dict)."""
+    if process_group is None:
+        return dict(sorted(local.items()))
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object({k: v.cpu() for k, v in local.items()}, gathered, dst=0, group=process_group)
+    if rank != 0:
+        return None
+    merged: Dict[str, torch.Tensor] = {}
+    for d in gathered:
+        for k, v in d.items():
+            if k in merged:
+                raise RuntimeError(f"merge_label_dicts: video {k} was scored by two ranks")
+            merged[k] = v
+    return dict(sorted(merged.items()))
 
 
 def co_teaching_round(corpus: "DeviceCorpus", stn: "TrainStep", ltn: "TrainStep", steps_per_epoch: Optional[int] = None,

@@ -619,3 +619,74 @@ def adagrad_step(param: torch.Tensor, grad: torch.Tensor, state_sum: torch.Tenso
                                float(eps), float(grad_scale), _p(grad_scale_dev), _stream())
     _lib.check(st, "lstc_adagrad_step")
     LAUNCHES.add(1)
+
+
+# ------------------------------------------------------------------------------------------ multi-tensor launches
+def _ptr_table(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+
+def _i64_table(vals):
+    import ctypes
+    return (ctypes.c_int64 * len(vals))(*vals)
+
+
+def multi_pack_bf16(srcs, flat: torch.Tensor, offsets) -> None:
+    """fp32 tensors `srcs` -> bf16 `flat[offsets[i] : offsets[i] + srcs[i].numel()]` in one launch (offsets in elements,
+    multiples of 8)."""
+    lib = _lib.load()
+    _cuda(flat, "flat", BF16)
+    for t in srcs:
+        _cuda(t, "src", F32)
+        if not t.is_contiguous():
+            raise RuntimeError("lstc_vad_b200.multi_pack_bf16: sources must be contiguous")
+    n = len(srcs)
+    base = flat.data_ptr()
+    st = lib.lstc_multi_pack_bf16(_ptr_table([t.data_ptr() for t in srcs]), _i64_table([t.numel() for t in srcs]), n,
+                                  _ptr_table([base + 2 * int(o) for o in offsets]), _stream())
+    _lib.check(st, "lstc_multi_pack_bf16")
+    LAUNCHES.add((n + 47) // 48)
+
+
+def multi_unpack_bf16(flat: torch.Tensor, offsets, dsts) -> None:
+    """bf16 `flat[offsets[i] : ...]` -> the fp32 tensors `dsts`, in one launch."""
+    lib = _lib.load()
+    _cuda(flat, "flat", BF16)
+    for t in dsts:
+        _cuda(t, "dst", F32)
+        if not t.is_contiguous():
+            raise RuntimeError("lstc_vad_b200.multi_unpack_bf16: destinations must be contiguous")
+    n = len(dsts)
+    base = flat.data_ptr()
+    st = lib.lstc_multi_unpack_bf16(_ptr_table([base + 2 * int(o) for o in offsets]),
+                                    _i64_table([t.numel() for t in dsts]), n,
+                                    _ptr_table([t.data_ptr() for t in dsts]), _stream())
+    _lib.check(st, "lstc_multi_unpack_bf16")
+    LAUNCHES.add((n + 47) // 48)
+
+
+def multi_adagrad(params, grads, states, lrs, weight_decay: float, eps: float = 1e-10, grad_scale: float = 1.0,
+                  grad_scale_dev: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.Adagrad step of every (param, grad, state) triple in ONE launch per 48 tensors.  `grads` are fp32
+    tensors, or all bf16 (slices of a reduced data-parallel bucket)."""
+    import ctypes
+    lib = _lib.load()
+    n = len(params)
+    if n == 0:
+        return
+    g_bf16 = grads[0].dtype == BF16
+    for p_, g_, s_ in zip(params, grads, states):
+        _cuda(p_, "param", F32)
+        _cuda(s_, "state", F32)
+        _cuda(g_, "grad", BF16 if g_bf16 else F32)
+        if not (p_.is_contiguous() and g_.is_contiguous() and s_.is_contiguous()):
+            raise RuntimeError("lstc_vad_b200.multi_adagrad: tensors must be contiguous")
+        if g_.numel() != p_.numel() or s_.numel() != p_.numel():
+            raise RuntimeError("lstc_vad_b200.multi_adagrad: size mismatch")
+    st = lib.lstc_multi_adagrad(_ptr_table([t.data_ptr() for t in params]), _ptr_table([t.data_ptr() for t in grads]),
+                                1 if g_bf16 else 0, _ptr_table([t.data_ptr() for t in states]),
+                                _i64_table([t.numel() for t in params]), (ctypes.c_float * n)(*[float(x) for x in lrs]),
+                                n, float(weight_decay), float(eps), float(grad_scale), _p(grad_scale_dev), _stream())
+    _lib.check(st, "lstc_multi_adagrad")
+    LAUNCHES.add((n + 47) // 48)
