@@ -211,6 +211,59 @@ def test_ltn_full_width_against_oracle(M, L, name):
         rel_close(f"{name} cls grad {k}", p.grad, csd[k].grad, 6e-2)
 
 
+@pytest.mark.parametrize("name", ["C2_ltn_sht", "C3_ltn_ucf"])
+def test_ltn_gradients_against_bf16_faithful_oracle(M, L, name):
+    """Tight gradient check.  The fp32 oracle can only bound the gradients at the reference's own bf16 floor (2.5e-1); a
+    wrong scale factor on one branch of the composition would hide below that.  Here the oracle rounds its forward to
+    bf16 at exactly the points where the CUDA path stores bf16 tensors (oracle.bf16_rounding), so forward activations
+    agree to accumulation order and what remains is the bf16 rounding INSIDE the backward (dS, dqkv, dY between
+    kernels): relative L2 error <= 3e-2 on every parameter gradient and on the input gradient."""
+    from oracle import lstc_oracle as O
+    kw, B, P, T, N = SHAPES[name]
+    D = kw["d_model"]
+    torch.manual_seed(0)
+    enc = M.Encoder(**kw)
+    cls = M.Classifier(D, 0.6, weight_init=True)
+    enc_sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    cls_sd = {k: v.clone() for k, v in cls.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2 * B * P, T * N, D, generator=g).abs()
+    labs = O.soft_labels((torch.rand(B, P * T, generator=g) > 0.9).float(), B, P, T)
+    cfg = O.EncoderConfig(**{k: v for k, v in kw.items() if k in O.EncoderConfig.__dataclass_fields__})
+    esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in enc_sd.items()}
+    csd = {k: v.clone().requires_grad_(True) for k, v in cls_sd.items()}
+    xo = x.clone().requires_grad_(True)
+    with O.bf16_rounding():
+        ref_loss, aux = O.ltn_train_loss(esd, csd, xo, labs, cfg, B, P)
+    ref_loss.backward()
+    enc, cls = enc.cuda().eval(), cls.cuda().eval()
+    args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=T, lambda_1=0.01)
+    xc = x.cuda().requires_grad_(True)
+    out = enc(xc)
+    probs = cls(out[:, 0, :].float().view([2 * B, P, D])).view(2 * B * P, -1)
+    # forward: bf16-faithful scores agree an order of magnitude tighter than against the fp32 oracle
+    assert (probs.detach().cpu() - aux["probs"].detach()).abs().max().item() < 2e-3
+    loss = L.get_MIL_loss(args, probs[:, 1])[0] + 0.8 * L.get_CE_loss(args, probs, labs.cuda())
+    assert abs(loss.item() - ref_loss.item()) < 2e-3
+    loss.backward()
+
+    def rel_l2(got, ref):
+        got, ref = got.detach().cpu().double(), ref.detach().double()
+        return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+    worst = {}
+    assert rel_l2(xc.grad, xo.grad) < 3e-2, ("x.grad", rel_l2(xc.grad, xo.grad))
+    for k, p in list(enc.named_parameters()) + [("cls." + k, p) for k, p in cls.named_parameters()]:
+        ref = (csd[k[4:]] if k.startswith("cls.") else esd[k]).grad
+        if ref is None:
+            assert p.grad is None, k
+            continue
+        worst[k] = rel_l2(p.grad, ref)
+    bad = {k: v for k, v in worst.items() if v >= 3e-2}
+    assert not bad, bad
+    assert len(worst) > 40
+
+
 def test_stn_odd_hidden_width_3027(M):
     """STN default n_hidden 3027 (Train/spatio_transformer_shanghaitech.py:216): not a multiple of 8, handled by
     zero-padding the cached bf16 weights; state_dict keeps [3027,2048] / [2048,3027]."""
@@ -334,3 +387,55 @@ def test_forward_cls_fast_path_equals_full_path(M, L, name):
     tensor_close(f"{name} cls x.grad", xg1, xg0, rel_l2=1e-1, p999=1e-1, max_rel=0.3)
     for k in g0:
         tensor_close(f"{name} cls grad {k}", g1[k], g0[k], rel_l2=1e-1, p999=1e-1, max_rel=0.5)
+
+
+@pytest.mark.parametrize("learned", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patch_embedding_class(M, learned, dtype):
+    """models/PatchEmbedding.py:12-19 through the drop-in CLASS (the reference never instantiates it; Encoder inlines the
+    same prepend): forward and backward against the torch expression, mean-token and learned-token variants."""
+    torch.manual_seed(3)
+    W, L0, D = 5, 48, 256
+    pe = M.PatchEmbedding(embed_dim=D, CLS_learned=learned).cuda()
+    assert [n for n, _ in pe.named_parameters()] == (["cls_token"] if learned else [])
+    x = torch.randn(W, L0, D, device="cuda").abs().to(dtype).requires_grad_(True)
+    out = pe(x)
+    assert out.dtype == dtype and tuple(out.shape) == (W, L0 + 1, D)
+    xr = x.detach().float().requires_grad_(True)
+    tok = pe.cls_token.detach().clone().requires_grad_(True) if learned else None
+    cls = tok.expand(W, -1, -1) if learned else torch.mean(xr, dim=1, keepdim=True)
+    ref = torch.cat([cls, xr], dim=1)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(out.float(), ref, rtol=tol, atol=tol)
+    assert torch.equal(out[:, 1:].float(), x.detach().float())   # the tokens themselves pass through untouched
+    g = torch.randn(W, L0 + 1, D, device="cuda")
+    out.float().backward(g)
+    ref.backward(g)
+    assert torch.allclose(x.grad.float(), xr.grad, rtol=tol, atol=tol)
+    if learned:
+        assert torch.allclose(pe.cls_token.grad, tok.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_mil_loss_flat_column_form_of_spatio_MIL_CE(L):
+    """Train/spatio_transformer_MIL_CE.py:32-44 as called at :176-178 for the non-UCF datasets: the Regressor output stays
+    a [2*B*P*T, 1] COLUMN and part_len = T > 1 is passed explicitly, so the bag score is max over P of the mean over T
+    while the sparsity term `mean(y_pred[B:])` slices ROWS of the column: every score but the first B (not the abnormal
+    half).  Loss, its two logged terms and the gradient against the torch expression of the reference."""
+    import torch.nn.functional as F
+    B, P, T = 4, 5, 3
+    args = types.SimpleNamespace(batch_size=B, part_num=P, part_len=7, lambda_1=0.01)   # args.part_len must be ignored
+    torch.manual_seed(11)
+    y = torch.rand(2 * B * P * T, 1, device="cuda").requires_grad_(True)
+    loss, err, l1 = L.get_MIL_loss(args, y, T)
+    yr = y.detach().clone().requires_grad_(True)
+    topk = torch.max(torch.mean(yr.view([B * 2, P, T]), dim=-1), dim=-1)[0]
+    nor, abn = topk[:B], topk[B:]
+    e = sum(torch.sum(F.relu(1 - abn + nor[i])) for i in range(B)) / B ** 2
+    sp = torch.mean(yr[B:])
+    ref = e + 0.01 * sp
+    assert abs(loss.item() - ref.item()) < 1e-6 and abs(err.item() - e.item()) < 1e-6 and abs(l1.item() - sp.item()) < 1e-6
+    loss.backward()
+    ref.backward()
+    assert torch.allclose(y.grad, yr.grad, rtol=1e-5, atol=1e-7)
+    # the quirk itself: rows 0..B-1 get no sparsity gradient, row B (still a NORMAL clip) does
+    assert (yr.grad[B:, 0] >= 0.01 / (2 * B * P * T - B) - 1e-9).all()

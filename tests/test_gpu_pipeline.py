@@ -315,3 +315,16 @@ def test_co_teaching_round_runs_the_four_phases():
     assert np.isfinite(out["stn_loss"]) and np.isfinite(out["ltn_loss"])
     assert not torch.equal(w_before, ltn.encoder.layer_stack[0].pos_ffn.w_1.weight.detach())
     assert set(out["seconds"]) == {"stn_epoch", "stn_labels", "ltn_epoch", "ltn_labels"}
+
+
+def test_roc_auc_delta_at_headline_width():
+    """BASELINE metric, second half: ROC-AUC within 1e-3 of the reference path at d_model 2048 (LTN-SHT shape: 49 tokens,
+    3 layers, 8 heads, n_hidden 4096) - briefly trained weights, a fixed synthetic split of 192 windows, CUDA path against
+    the fp32 CPU oracle (the same routine fills the `auc_delta` key of the bench line)."""
+    import bench
+    from lstc_vad_b200.harness import WORKLOADS
+    r = bench.auc_delta_vs_oracle(WORKLOADS["ltn_sht"], torch.device("cuda", 0), train_steps=8, test_windows=192)
+    assert r["windows"] == 192 and r["d_model"] == 2048
+    assert 0.55 < r["auc_oracle_fp32"] <= 1.0, r      # the briefly trained model separates the split (non-degenerate AUC)
+    assert r["value"] <= 1e-3, r
+    assert r["score_max_abs_diff"] < 3e-2, r
