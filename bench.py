@@ -514,6 +514,16 @@ def main():
     o1.record()
     sync_all()
     ms_opt = o0.elapsed_time(o1)
+    # the optimizer launch alone (one multi-tensor Adagrad kernel over every parameter: 5 passes over 407 MB, far larger
+    # than L2), timed directly - differences between whole-step passes are dominated by power-cap clock noise
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(10):
+        step.opt.step()
+    k1.record()
+    sync_all()
+    ms_opt_kernel = k0.elapsed_time(k1) / 10
+    n_params = sum(p_.numel() for p_ in step.parameters() if p_.grad is not None)
     step.opt = None
 
     # ---------------- opt-in CLS fast path (Encoder.forward_cls): same loss / gradients, last layer's dead work skipped ------
@@ -652,7 +662,9 @@ def main():
                                "ms_per_step": (ms_opt_graph if ms_opt_graph != inf else ms_opt) / steps,
                                "launch": "cuda_graph" if ms_opt_graph != inf else "eager",
                                "eager_ms_per_step": ms_opt / steps,
-                               "optimizer_ms_per_step": ((ms_opt_graph - ms_graph) / steps) if (ms_opt_graph != inf and use_graph) else None,
+                               "optimizer_kernel_ms": ms_opt_kernel,
+                               "optimizer_kernel_gbs": 5 * 4 * n_params / (ms_opt_kernel * 1e-3) / 1e9,
+                               "optimizer_ms_per_step_by_difference": ((ms_opt_graph - ms_graph) / steps) if (ms_opt_graph != inf and use_graph) else None,
                                "what": "fwd+bwd + gradient reduce + ONE multi-tensor fused Adagrad launch (lr 1e-4 / "
                                        "1e-2, weight decay 1e-3) captured in the same CUDA graph, inputs resident"},
             "cls_fast_path": {"value": total_windows / (ms_cls * 1e-3), "unit": UNIT, "ms_per_step": ms_cls / steps,

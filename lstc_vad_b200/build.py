@@ -63,7 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         s = CSRC / src
         if not force and obj.exists() and obj.stat().st_mtime > max(s.stat().st_mtime, common_t):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(s), "-o", str(obj)]
+        extra = os.environ.get("LSTC_NVCC_EXTRA", "").split()  # e.g. -DLSTC_ATTN_TIMING for the pipeline accounting
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-c", str(s), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -673,10 +673,10 @@ static int dispatch_lp(bool bwd, const Params& p, cudaStream_t stream) {
   return LSTC_ERR_UNSUPPORTED;
 }
 
-// Implementation choice.  Default: the tcgen05 / TMEM kernels of attention_tc.cu for windows of up to 64 tokens (their
-// software-pipelined sub-tile kernel), the mma.sync kernels of this file for 65..96 tokens (measured on B200 at L = 81:
-// 0.55 / 1.50 ms against 0.58 / 1.59 ms of the single-buffered M = 128 tcgen05 kernel).  LSTC_ATTN_IMPL=mma | tc forces one
-// implementation for every length (A/B measurements).
+// Implementation choice.  Default: the tcgen05 / TMEM kernels of attention_tc.cu for every supported length (measured
+// on B200, dropout + bias, fwd / bwd per layer: L = 49 0.18 / 0.40 ms against 0.26 / 0.61 ms of the mma.sync kernels of
+// this file, L = 81 0.42 / 0.93 ms against 0.55 / 1.50 ms).  LSTC_ATTN_IMPL=mma selects the mma.sync kernels
+// (A/B measurements); LSTC_ATTN_IMPL=tc is the default spelled out.
 static int attn_impl_override() {
   static const int v = [] {
     const char* e = getenv("LSTC_ATTN_IMPL");
@@ -690,7 +690,7 @@ static int attn_impl_override() {
 
 static int dispatch(bool bwd, const Params& p, int dk, cudaStream_t stream) {
   const int force = attn_impl_override();
-  if (force == 2 || (force == 0 && p.L <= 64)) return attn_tc::run(bwd, p, dk, stream);
+  if (force != 1) return attn_tc::run(bwd, p, dk, stream);
   switch (dk) {
     case 64: return dispatch_lp<64>(bwd, p, stream);
     case 128: return dispatch_lp<128>(bwd, p, stream);

@@ -6,28 +6,30 @@
 //   O = P v ; O.transpose(1,2).contiguous().view(W, L, H*dv)
 // and its autograd backward.
 //
-// A window has L <= 96 tokens, far below the 128 rows of a tcgen05 tile, so a TILE stacks G = 128 / LP windows of one
-// head (LP = 32, 64 or 128 rows per window, rows >= L zero-filled by TMA): one [G][LP][64] box of q / k / v / dO is a
-// [128 x 64] SWIZZLE_128B operand tile.  Scores of the G windows are the diagonal LP x LP blocks of one 128 x 128
-// product; probabilities go back to shared memory as a block-diagonal bf16 matrix P (off-diagonal blocks stay zero), so
-// that P V, dS K, dS^T Q and P^T dO of all G windows are again single 128-row products:
+// A window has L <= 96 tokens, far below the 128 rows of a tcgen05 tile.  Two kernels (see the comment above each):
+//   attn_tc64_kernel  (L <= 64): a TILE stacks G = 128 / LP windows of one head (LP = 32 or 64 rows per window, rows
+//                     >= L zero-filled by TMA); M = 64 products per 64-row sub-tile, both sub-tiles share TMEM columns
+//   attn_tc128_kernel (65..96) : one window per tile, M = 128 products
+// Common design: one [G][LP][64] TMA box of q / k / v / dO is a SWIZZLE_128B operand tile; probabilities go back to
+// shared memory as bf16 operands (block-diagonal when several windows share a product), so that
 //   forward : S = sum_c Q_c K_c^T (c = 64-column chunks of dk)  -> softmax / dropout -> O_c = P V_c
 //   backward: S = sum_c Q_c K_c^T ; dP = sum_c dO_c V_c^T       -> P, dS            -> dQ_c = dS K_c ;
-//             dK_c = dS^T Q_c ; dV_c = P^T dO_c                     (K, Q, dO chunks re-read through L2)
+//             dK_c = dS^T Q_c ; dV_c = P^T dO_c                     (K, Q, dO chunks re-read through L2, kept there
+//                                                                    by evict-last / evict-first TMA cache hints)
 // The same shared-memory tile serves as K-major operand (row = token: Q K^T, dO V^T), as MN-major B operand (token =
 // reduction index: P V, dS K, ...) and P / dS as K-major or MN-major A operand (dS vs dS^T) purely through the UMMA
 // descriptors - nothing is ever transposed in memory.
 //
-// One persistent CTA per SM (grid = (CTAs per head, heads)), 10 warps, no CTA-wide barrier after start-up:
-//   warp 0     TMA producer: [128 x 64] tiles into an n-stage ring (full / empty mbarriers), runs ahead across tiles
-//   warp 1     tcgen05.mma issuer (one thread), owns the 512 TMEM columns
-//   warps 2-5  softmax: thread = one score row (tcgen05.ld 32x32b: no shuffles), online max / sum, Philox dropout,
-//              dS = P (dP - sum P dP); bf16 P / dS into the block-diagonal smem operands; the rel-pos bias gradient is
-//              accumulated in TMEM columns over all tiles of the CTA and flushed once with atomics
-//   warps 6-9  epilogue: accumulator chunk (TMEM) -> bf16 -> swizzled smem staging tile -> TMA store (the tensor map
-//              clips rows >= L and windows >= W)
-// TMEM columns: S [0,128) ; forward: 4 accumulator slots [128,384) ; backward: dP [128,256), 2 accumulator slots
-// [256,384), bias gradient [384,512).
+// One persistent CTA per SM (grid = (CTAs per head, heads)), warp-specialised, no CTA-wide barrier after start-up:
+//   TMA producer   [rows x 64] tiles into an n-stage ring (full / empty mbarriers), runs ahead across tiles, in exactly
+//                  the order the MMA warp consumes them
+//   MMA issuer     one thread; S (and dP) are double-buffered in TMEM so the score products of later tiles are issued
+//                  before the softmax of the current one has finished; owns the 512 TMEM columns
+//   softmax warps  thread = one score row (tcgen05.ld 32x32b: no shuffles), Philox dropout, dS = P (dP - sum P dP);
+//                  packed bf16 P / dS into the smem operands; the rel-pos bias gradient is accumulated in TMEM columns
+//                  over all tiles of the CTA and flushed once with atomics
+//   epilogue warps accumulator chunk (TMEM) -> bf16 -> swizzled smem staging tile -> TMA store (the tensor map clips
+//                  rows >= L and windows >= W)
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,13 +45,34 @@ namespace attn_tc {
 using attn::Params;
 using namespace ptx;
 
-constexpr int NUM_THREADS = 320;    // M = 128 kernel (L > 64)
-constexpr int NUM_THREADS64 = 384;  // sub-tile kernel (L <= 64)
+constexpr int NUM_THREADS64 = 384;   // 12 warps = 3 warpgroups (setmaxnreg re-allocates registers per warpgroup)
+constexpr int NUM_THREADS128 = 512;  // 16 warps = 4 warpgroups (second epilogue group)
 constexpr uint32_t TILE_B = 16384;  // [128 rows][64 bf16]
 constexpr uint32_t PANEL_B = 16384; // one 64-column panel of the [128 x 128] P / dS operand
-constexpr int MAX_STAGES = 12;
+constexpr int MAX_STAGES = 16;
 constexpr uint32_t SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
-constexpr uint32_t BAR_BYTES = 512;
+constexpr uint32_t BAR_BYTES = 1024;
+
+// Optional pipeline accounting (build with -DLSTC_ATTN_TIMING): CTA (0,0) prints, per role, the cycles it spent waiting
+// on each barrier class - the quickest way to see which stage of the producer / MMA / softmax / epilogue pipeline is the
+// critical one.  Off in normal builds (the macros compile to nothing).
+#ifdef LSTC_ATTN_TIMING
+#define TWAIT(acc, stmt)               \
+  do {                                 \
+    const long long _t0 = clock64();   \
+    stmt;                              \
+    (acc) += clock64() - _t0;          \
+  } while (0)
+#define TDECL(...) long long __VA_ARGS__
+#define TPRINT(...)                                  \
+  do {                                               \
+    if (blockIdx.x == 0 && blockIdx.y == 0) printf(__VA_ARGS__); \
+  } while (0)
+#else
+#define TWAIT(acc, stmt) stmt
+#define TDECL(...)
+#define TPRINT(...)
+#endif
 
 struct TcParams {
   Params p;
@@ -57,7 +80,9 @@ struct TcParams {
   int nkeys;       // N of the score product (multiple of 16): 128 when G > 1, round_up(L, 16) when G == 1
   int ks_tok;      // UMMA_K steps over the token (reduction) dim of P V, dS K, dS^T Q, P^T dO
   int npiece;      // 32-column pieces of one score row
-  int n_stages;    // ring depth
+  int n_stages;    // total ring depth = n_stages_a + n_stages_b
+  int n_stages_a;  // stages of the score-operand ring (q, k, dO, v of the S / dP products: HBM-bound)
+  int n_stages_b;  // stages of the chunk-operand ring (forward: v ; backward: k, q, dO re-read through L2)
   int bias_pitch;  // floats per row of the shared-memory bias copy (odd -> conflict-free column reads)
   uint32_t bias_bytes;
 };
@@ -88,71 +113,116 @@ __device__ __forceinline__ void store_piece_bf16(uint32_t base, int r, int cb, c
   }
 }
 
-template <int LP, int DK, bool BWD>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_tc_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-               const __grid_constant__ CUtensorMap tm_out) {
-  constexpr int G = 128 / LP;
+// writes 32 consecutive bf16 values (16 packed words) of row r starting at column cb of a two-panel operand
+__device__ __forceinline__ void store_piece_packed(uint32_t base, int r, int cb, const uint32_t* w) {
+  const uint32_t pb = base + (uint32_t)(cb >> 6) * PANEL_B;
+  const int c0 = (cb & 63) >> 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) st_shared_v4(pb + sw128(r, c0 + c), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+}
+
+// ==========================================================================================================
+// Windows of 65..96 tokens: one window per tile, M = 128 products (an M = 64 instruction costs the same tensor-pipe
+// time, so two sub-tile products per window would double it), software-pipelined like the sub-tile kernel below:
+//   forward  MMA order: S(0), S(1) ; for t: [wait P(t)], { P V_c(t), S_c(t+2) } per chunk c
+//   backward MMA order: S(0), dP(0), S(1) ; for t: [wait P(t)], dP(t+1), { dQ_c dK_c dV_c (t), S_c(t+2) } per chunk c
+// S is double-buffered in TMEM (96 columns each); dP is not (there is no room), so dP(t+1) is issued first thing after
+// the softmax of tile t has released it.  A score row has up to 96 columns - too many to keep e, dP and both packed
+// operands in registers - so the softmax works in 32-column pieces and uses the S / dP columns themselves as scratch:
+// e = exp2(x - max) is written back over S, t = P_dropped * dP over dP.
+// Ring stages hold only nkeys = round_up(L, 16) rows (the 128-row A operand of a score product then reads the next
+// stage's rows as its rows nkeys..127: finite garbage that only reaches accumulator rows nobody stores); rows of
+// padding are forced to exact zeros in P / dS (they are reduction indices of dK = dS^T Q and dV = P^T dO).
+// TMEM columns: S[2] 0, 96 ; forward: accumulator slots 192 + 64 a (a < 4)
+//               backward: dP 192 ; slots 288, 352 ; bias gradient 416..511
+// Warps: 0-3 softmax (thread = score row = TMEM lane), 4-7 epilogue, 8 TMA producer, 9 MMA issuer, 10-11 idle.
+// ==========================================================================================================
+template <int DK, bool BWD>
+__global__ void __launch_bounds__(NUM_THREADS128, 1)
+attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                  const __grid_constant__ CUtensorMap tm_out) {
   constexpr int NC = DK / 64;
   constexpr int NACC = BWD ? 2 : 4;
-  constexpr uint32_t ACC_COL0 = BWD ? 256u : 128u;
-  constexpr uint32_t DP_COL0 = 128u, DB_COL0 = 384u;
-  constexpr int MAXP = (G > 1) ? LP / 32 : 3;
+  constexpr int NPIECE = 3;                 // 32-column pieces of a score row (96 columns)
   constexpr int NPROD = BWD ? 3 * NC : NC;
+  constexpr uint32_t S_N = 96;              // N of the score products (keys nkeys..95: finite garbage, masked by the bias)
+  constexpr uint32_t DP_COL0 = 192u, DB_COL0 = 416u;
+  constexpr int BIAS_PITCH_W = 49;          // words (bf16 pairs) per bias row: odd -> conflict-free column reads
   constexpr float LOG2E = 1.4426950408889634f;
+  auto acc_col = [](uint32_t a) -> uint32_t { return (BWD ? 288u : 192u) + 64u * a; };
 
   Params p = tp.p;
   p.offset += rng_step();
-  const int NS = tp.n_stages;
+  const int NS = tp.n_stages, NSA = tp.n_stages_a, NSB = tp.n_stages_b;
   const int L = p.L;
   const int h = blockIdx.y;
   const int HD = p.H * DK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t STAGE_B = (uint32_t)tp.nkeys * 128u;
+  const int KS = tp.ks_tok;
 
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t sRing = s0;
-  const uint32_t sP = sRing + (uint32_t)NS * TILE_B;
-  const uint32_t sDS = sP + 2 * PANEL_B;  // backward only
+  const uint32_t sP = sRing + (uint32_t)NS * STAGE_B;
+  const uint32_t sDS = sP + 2 * PANEL_B;
   const uint32_t sStg = BWD ? sDS + 2 * PANEL_B : sDS;
   const uint32_t sBias = sStg + 2 * TILE_B;
   const uint32_t sBar = sBias + tp.bias_bytes;
-  auto full_bar = [&](int s) { return sBar + 8u * s; };
-  auto empty_bar = [&](int s) { return sBar + 8u * (MAX_STAGES + s); };
-  const uint32_t s_full = sBar + 8u * (2 * MAX_STAGES), p_full = s_full + 8u;
-  auto acc_full = [&](int a) { return sBar + 8u * (2 * MAX_STAGES + 2 + a); };
-  auto acc_empty = [&](int a) { return sBar + 8u * (2 * MAX_STAGES + 6 + a); };
-  const uint32_t tmem_slot = sBar + 8u * (2 * MAX_STAGES + 10);
-  float* bias_s = reinterpret_cast<float*>(smem + (sBias - smem_u32(smem)));
+  // two operand rings with their own producer and issuer thread each: A = operands of the score products, B = operands of
+  // the chunk products; ring B's stages follow ring A's in shared memory
+  const uint32_t sRingB = sRing + (uint32_t)NSA * STAGE_B;
+  auto full_a = [&](int s) { return sBar + 8u * s; };
+  auto empty_a = [&](int s) { return sBar + 8u * (MAX_STAGES + s); };
+  auto full_b = [&](int s) { return sBar + 8u * (2 * MAX_STAGES + s); };
+  auto empty_b = [&](int s) { return sBar + 8u * (3 * MAX_STAGES + s); };
+  auto s_full = [&](uint32_t b) { return sBar + 8u * (4 * MAX_STAGES + b); };
+  const uint32_t p_full = sBar + 8u * (4 * MAX_STAGES + 2), p_empty = p_full + 8u, dp_full = p_full + 16u;
+  auto acc_full = [&](int a) { return sBar + 8u * (4 * MAX_STAGES + 5 + a); };
+  auto acc_empty = [&](int a) { return sBar + 8u * (4 * MAX_STAGES + 9 + a); };
+  const uint32_t tmem_slot = sBar + 8u * (4 * MAX_STAGES + 13);
+  uint32_t* bias_w = reinterpret_cast<uint32_t*>(smem + (sBias - smem_u32(smem)));
 
-  // ---------------- start-up ----------------
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_out);
     if (BWD) tma_prefetch_desc(&tm_do);
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < NSA; ++s) {
+      mbar_init(full_a(s), 1);
+      mbar_init(empty_a(s), 1);
     }
-    mbar_init(s_full, 1);
+    for (int s = 0; s < NSB; ++s) {
+      mbar_init(full_b(s), 1);
+      mbar_init(empty_b(s), 1);
+    }
+    mbar_init(s_full(0), 1);
+    mbar_init(s_full(1), 1);
     mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(dp_full, 1);
     for (int a = 0; a < NACC; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), 4);
+      mbar_init(acc_empty(a), 4);  // the 4 warps of the epilogue group that drains this slot (slot parity = group)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   {
-    // the block-diagonal operands start (and, off the diagonal blocks, stay) all zero
-    const uint32_t nbytes = (BWD ? 4u : 2u) * PANEL_B;
-    for (uint32_t o = threadIdx.x * 16u; o < nbytes; o += NUM_THREADS * 16u) st_shared_v4(sP + o, make_uint4(0, 0, 0, 0));
-    if (p.bias != nullptr) {
-      const float* bsrc = p.bias + (int64_t)h * L * L;
-      for (int idx = threadIdx.x; idx < L * L; idx += NUM_THREADS) {
-        const int r = idx / L;
-        bias_s[r * tp.bias_pitch + (idx - r * L)] = __ldg(bsrc + idx);
+    // ring + block-diagonal operands start all zero: rows a product reads beyond a stage's nkeys rows (the next stage,
+    // or the P buffer after the last one) are then always finite values, never stale NaN bit patterns
+    const uint32_t nbytes = (uint32_t)NS * STAGE_B + (BWD ? 4u : 2u) * PANEL_B;  // NS = NSA + NSB: both rings
+    for (uint32_t o = threadIdx.x * 16u; o < nbytes; o += NUM_THREADS128 * 16u) st_shared_v4(sRing + o, make_uint4(0, 0, 0, 0));
+    // bias rows as bf16 pairs: bias * log2e (0 without a bias) in the columns < L, -inf in the padding columns
+    const float* bsrc = p.bias != nullptr ? p.bias + (int64_t)h * L * L : nullptr;
+    for (int idx = threadIdx.x; idx < L * 48; idx += NUM_THREADS128) {
+      const int r = idx / 48, j = idx - r * 48;
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = 2 * j + e;
+        v[e] = c < L ? (bsrc != nullptr ? __ldg(bsrc + r * L + c) * LOG2E : 0.f) : -INFINITY;
       }
+      bias_w[r * BIAS_PITCH_W + j] = pack_bf16x2(v[0], v[1]);
     }
   }
   fence_proxy_async();
@@ -161,307 +231,379 @@ attn_tc_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, co
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const int n_my = ((int)blockIdx.x < tp.tiles) ? (tp.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp >= 8 && warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+  }
+  if (warp == 8 || warp == 11) {
+    // ===================== TMA producers: warp 8 feeds ring A, warp 11 ring B, each in its issuer's order =====================
     if (lane == 0) {
+      const bool ring_a = warp == 8;
+      const int n_s = ring_a ? NSA : NSB;
+      const uint32_t base = ring_a ? sRing : sRingB;
       int s = 0;
       uint32_t ph = 0;
-      auto load = [&](const CUtensorMap* tm, int col, int w0) {
-        mbar_wait(empty_bar(s), ph ^ 1u, 1);
-        mbar_arrive_expect_tx(full_bar(s), TILE_B);
-        tma_load_3d(sRing + (uint32_t)s * TILE_B, tm, full_bar(s), col, 0, w0);
-        if (++s == NS) { s = 0; ph ^= 1u; }
+      TDECL(w_empty = 0, t_begin = clock64());
+      auto load = [&](const CUtensorMap* tm, int col, int w0, uint64_t policy) {
+        const uint32_t fb = ring_a ? full_a(s) : full_b(s);
+        TWAIT(w_empty, mbar_wait(ring_a ? empty_a(s) : empty_b(s), ph ^ 1u, 1));
+        mbar_arrive_expect_tx(fb, STAGE_B);
+        tma_load_3d_hint(base + (uint32_t)s * STAGE_B, tm, fb, col, 0, w0, policy);
+        if (++s == n_s) { s = 0; ph ^= 1u; }
       };
+      const uint64_t pol_again = BWD ? L2_EVICT_LAST : L2_EVICT_FIRST, pol_once = L2_EVICT_FIRST;
       const int cq = h * DK, ck = HD + h * DK, cv = 2 * HD + h * DK;
-      for (int t = blockIdx.x; t < tp.tiles; t += gridDim.x) {
-        const int w0 = t * G;
-        for (int c = 0; c < NC; ++c) {
-          load(&tm_qkv, cq + 64 * c, w0);
-          load(&tm_qkv, ck + 64 * c, w0);
+      auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+      if (ring_a) {
+        auto load_s = [&](int it, int c) {
+          load(&tm_qkv, cq + 64 * c, tile_of(it), pol_again);
+          load(&tm_qkv, ck + 64 * c, tile_of(it), pol_again);
+        };
+        auto load_dp = [&](int it, int c) {
+          load(&tm_do, cq + 64 * c, tile_of(it), pol_again);
+          load(&tm_qkv, cv + 64 * c, tile_of(it), pol_once);
+        };
+        if (n_my > 0) {
+          for (int c = 0; c < NC; ++c) load_s(0, c);
+          if (BWD)
+            for (int c = 0; c < NC; ++c) load_dp(0, c);
         }
-        if (BWD) {
-          for (int c = 0; c < NC; ++c) {
-            load(&tm_do, cq + 64 * c, w0);
-            load(&tm_qkv, cv + 64 * c, w0);
-          }
-          for (int c = 0; c < NC; ++c) {
-            load(&tm_qkv, ck + 64 * c, w0);
-            load(&tm_qkv, cq + 64 * c, w0);
-            load(&tm_do, cq + 64 * c, w0);
-          }
-        } else {
-          for (int c = 0; c < NC; ++c) load(&tm_qkv, cv + 64 * c, w0);
+        if (n_my > 1)
+          for (int c = 0; c < NC; ++c) load_s(1, c);
+        for (int it = 0; it < n_my; ++it) {
+          if (BWD && it + 1 < n_my)
+            for (int c = 0; c < NC; ++c) load_dp(it + 1, c);
+          if (it + 2 < n_my)
+            for (int c = 0; c < NC; ++c) load_s(it + 2, c);
         }
+      } else {
+        for (int it = 0; it < n_my; ++it)
+          for (int c = 0; c < NC; ++c) {
+            if (BWD) {
+              load(&tm_qkv, ck + 64 * c, tile_of(it), pol_once);
+              load(&tm_qkv, cq + 64 * c, tile_of(it), pol_once);
+              load(&tm_do, cq + 64 * c, tile_of(it), pol_once);
+            } else {
+              load(&tm_qkv, cv + 64 * c, tile_of(it), pol_once);
+            }
+          }
       }
+      TPRINT("producer%d: total %lld cyc, waiting for a free stage %lld\n", (int)!ring_a, clock64() - t_begin, w_empty);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers =====================
+    // Two issuing threads with their own operand ring each: warp 9 issues the score products (S, dP), warp 10 the chunk
+    // products (P V, or dQ / dK / dV).  Every product is a handful of small MMAs behind two barrier waits and two
+    // commits - ~1 us of single-thread issue work for ~0.1 us of tensor-pipe time - so ONE issuer was the critical
+    // path of the whole kernel (17.5 k of 22 k cycles per tile at L = 81).
     if (lane == 0) {
-      const uint32_t id_s = idesc_bf16_m128((uint32_t)tp.nkeys, false, false);  // Q K^T, dO V^T
-      const uint32_t id_pk = idesc_bf16_m128(64u, false, true);                   // P V, dS K
-      const uint32_t id_ptk = idesc_bf16_m128(64u, true, true);                   // dS^T Q, P^T dO
-      const int KS = tp.ks_tok;
+      const bool do_a = warp == 9;
+      const int n_s = do_a ? NSA : NSB;
+      const uint32_t base = do_a ? sRing : sRingB;
+      const uint32_t id_s = idesc_bf16_m128(S_N, false, false);
+      const uint32_t id_pk = idesc_bf16_m128(64u, false, true);
+      const uint32_t id_ptk = idesc_bf16_m128(64u, true, true);
       int s = 0;
-      uint32_t ph = 0, nacc = 0, it = 0;
+      uint32_t ph = 0, nacc = 0;
+      TDECL(w_full = 0, w_acc = 0, w_p = 0, t_begin = clock64());
       auto acquire = [&]() -> uint32_t {
-        mbar_wait(full_bar(s), ph, 2);
-        const uint32_t a = sRing + (uint32_t)s * TILE_B;
-        return a;
+        TWAIT(w_full, mbar_wait(do_a ? full_a(s) : full_b(s), ph, 2));
+        return base + (uint32_t)s * STAGE_B;
       };
-      auto release = [&]() {  // the stage acquired last is free once the MMAs issued so far retire
-        umma_commit(empty_bar(s));
-        if (++s == NS) { s = 0; ph ^= 1u; }
-      };
-      // acc (128 x nkeys) (+)= A_tile[128 x 64] * B_tile[nkeys x 64]^T over two consecutive ring stages
-      auto score_product = [&](uint32_t tmem_d, bool first) {
+      auto advance = [&]() { if (++s == n_s) { s = 0; ph ^= 1u; } };
+      auto score_product = [&](uint32_t col, bool first) {
         const uint32_t a = acquire();
         const int sa = s;
-        if (++s == NS) { s = 0; ph ^= 1u; }
+        advance();
         const uint32_t b = acquire();
         tcgen05_fence_after();
         const uint64_t da = desc_kmajor(a), db = desc_kmajor(b);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2u * k, db + 2u * k, id_s, (!first || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(sa));
-        release();
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + col, da + 2u * k, db + 2u * k, id_s, (!first || k > 0) ? 1u : 0u);
+        umma_commit(empty_a(sa));
+        umma_commit(empty_a(s));
+        advance();
       };
-      // acc slot (128 x 64) = A (two-panel smem operand, K- or MN-major) * ring tile (MN-major B: token rows = k)
       auto chunk_product = [&](uint32_t a_base, bool a_mn) {
         const uint32_t b = acquire();
         const uint32_t slot = nacc % NACC;
-        mbar_wait(acc_empty(slot), ((nacc / NACC) & 1u) ^ 1u, 3);
+        TWAIT(w_acc, mbar_wait(acc_empty(slot), ((nacc / NACC) & 1u) ^ 1u, 3));
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + ACC_COL0 + 64u * slot;
+        const uint32_t d = tmem_base + acc_col(slot);
         const uint64_t db = desc_mnmajor(b, 8192u);
         if (a_mn) {
           const uint64_t da = desc_mnmajor(a_base, PANEL_B);
-          for (int j = 0; j < KS; ++j) umma_bf16(tmem_d, da + 128u * j, db + 128u * j, id_ptk, j > 0 ? 1u : 0u);
+          for (int j = 0; j < KS; ++j) umma_bf16(d, da + 128u * j, db + 128u * j, id_ptk, j > 0 ? 1u : 0u);
         } else {
-          for (int j = 0; j < KS; ++j) {
-            const uint64_t da = desc_kmajor(a_base + (uint32_t)(j >> 2) * PANEL_B) + 2u * (j & 3);
-            umma_bf16(tmem_d, da, db + 128u * j, id_pk, j > 0 ? 1u : 0u);
-          }
+          for (int j = 0; j < KS; ++j)
+            umma_bf16(d, desc_kmajor(a_base + (uint32_t)(j >> 2) * PANEL_B) + 2u * (j & 3), db + 128u * j, id_pk,
+                      j > 0 ? 1u : 0u);
         }
-        release();
+        umma_commit(empty_b(s));
+        advance();
         umma_commit(acc_full(slot));
         ++nacc;
       };
-      for (int t = blockIdx.x; t < tp.tiles; t += gridDim.x, ++it) {
-        for (int c = 0; c < NC; ++c) score_product(tmem_base, c == 0);
-        if (BWD)
-          for (int c = 0; c < NC; ++c) score_product(tmem_base + DP_COL0, c == 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, it & 1u, 4);
-        tcgen05_fence_after();
-        for (int c = 0; c < NC; ++c) {
-          if (BWD) {
-            chunk_product(sDS, false);  // dQ_c = dS K_c
-            chunk_product(sDS, true);   // dK_c = dS^T Q_c
-            chunk_product(sP, true);    // dV_c = P^T dO_c
-          } else {
-            chunk_product(sP, false);   // O_c = P V_c
+      if (do_a) {
+        auto phase_s = [&](int it) {
+          for (int c = 0; c < NC; ++c) score_product(S_N * ((uint32_t)it & 1u), c == 0);
+          umma_commit(s_full((uint32_t)it & 1u));
+        };
+        auto phase_dp = [&](int it) {
+          for (int c = 0; c < NC; ++c) score_product(DP_COL0, c == 0);
+          umma_commit(dp_full);
+        };
+        if (n_my > 0) {
+          phase_s(0);
+          if (BWD) phase_dp(0);
+        }
+        if (n_my > 1) phase_s(1);
+        for (int it = 0; it < n_my; ++it) {
+          // softmax of tile `it` done: S[it & 1] and dP are released
+          TWAIT(w_p, mbar_wait(p_full, (uint32_t)it & 1u, 4));
+          tcgen05_fence_after();
+          if (BWD && it + 1 < n_my) phase_dp(it + 1);
+          if (it + 2 < n_my) phase_s(it + 2);
+        }
+      } else {
+        for (int it = 0; it < n_my; ++it) {
+          TWAIT(w_p, mbar_wait(p_full, (uint32_t)it & 1u, 4));  // P / dS of tile `it` written
+          tcgen05_fence_after();
+          for (int c = 0; c < NC; ++c) {
+            if (BWD) {
+              chunk_product(sDS, false);  // dQ_c = dS K_c
+              chunk_product(sDS, true);   // dK_c = dS^T Q_c
+              chunk_product(sP, true);    // dV_c = P^T dO_c
+            } else {
+              chunk_product(sP, false);   // O_c = P V_c
+            }
           }
+          umma_commit(p_empty);  // P / dS may be overwritten once these products retire
         }
       }
+      TPRINT("mma%d    : total %lld cyc, waiting for operands %lld, for an accumulator slot %lld, for the softmax %lld (%d tiles)\n",
+             (int)!do_a, clock64() - t_begin, w_full, w_acc, w_p, n_my);
     }
-  } else if (warp < 6) {
+  } else if (warp < 4) {
     // ===================== softmax warps: thread = score row =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
     const int q = warp & 3;
-    const int r = q * 32 + lane;  // row of the tile = TMEM lane
-    const int g = r / LP, i = r - g * LP;
+    const int r = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t cb = (G > 1) ? (uint32_t)(g * LP) : 0u;  // first column of this row's diagonal block
-    const int npiece = (G > 1) ? MAXP : tp.npiece;
     const float sl2 = p.scale * LOG2E;
-    const bool has_bias = p.bias != nullptr;
     const bool drop = p.drop_p > 0.f;
-    const int ii = i < L ? i : L - 1;
-    const float* brow = bias_s + ii * tp.bias_pitch;
+    const bool want_db = BWD && p.dbias != nullptr;
+    const bool valid = r < L;
+    const uint32_t* brow = bias_w + (valid ? r : L - 1) * BIAS_PITCH_W;
     const int64_t ld8 = (L + 7) >> 3;
-    if (BWD && p.dbias != nullptr) {
+    const uint32_t thr_hi = p.drop_thr16 << 16;
+    if (want_db) {
       uint32_t z[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) z[j] = 0u;
 #pragma unroll
-      for (int k = 0; k < MAXP; ++k)
-        if (k < npiece) tmem_st_32x32b_x32(trow + DB_COL0 + 32u * k, z);
+      for (int k = 0; k < NPIECE; ++k) tmem_st_32x32b_x32(trow + DB_COL0 + 32u * k, z);
       tmem_st_wait();
     }
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < tp.tiles; t += gridDim.x, ++it) {
-      const int64_t w = (int64_t)t * G + g;
-      const bool valid = (i < L) && (w < p.W);
-      const int64_t grow = (w * p.H + h) * (int64_t)L + i;
-      mbar_wait(s_full, it & 1u, 5);
+    // x = (s scale + bias) log2e of one 32-column piece
+    auto scores_piece = [&](const uint32_t (&rs)[32], int k, float (&x)[32]) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const uint32_t w = brow[16 * k + jj];
+        x[2 * jj] = fmaf(__uint_as_float(rs[2 * jj]), sl2, bf16lo_to_f32(w));
+        x[2 * jj + 1] = fmaf(__uint_as_float(rs[2 * jj + 1]), sl2, bf16hi_to_f32(w));
+      }
+    };
+    TDECL(w_s = 0, w_dp = 0, w_pe = 0, t_begin = clock64());
+    for (int it = 0; it < n_my; ++it) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const uint32_t scol = S_N * ((uint32_t)it & 1u);
+      const int64_t grow = ((int64_t)t * p.H + h) * (int64_t)L + r;
+      TWAIT(w_s, mbar_wait(s_full((uint32_t)it & 1u), ((uint32_t)it >> 1) & 1u, 5));
       tcgen05_fence_after();
-      // ---- pass 1: v = (s * scale + bias) * log2e back into TMEM, online row max / sum ----
-      float m = -INFINITY, l = 0.f;
+      // The four passes below run as ROLLED loops over the three 32-column pieces (a fully unrolled body is ~60 KB of
+      // code: with one softmax warp per scheduler the instruction fetch, not the math, became the limit); the packed
+      // results of a piece are moved into their slice of pk / dk by a k-dispatched copy so the arrays stay in registers.
+      // ---- pass 1: row maximum ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int k = 0; k < NPIECE; ++k) {
+        uint32_t rs[32];
+        tmem_ld_32x32b_x32(trow + scol + 32u * k, rs);
+        tmem_ld_wait();
+        float x[32];
+        scores_piece(rs, k, x);
 #pragma unroll
-      for (int k = 0; k < MAXP; ++k) {
-        if (k < npiece) {
-          uint32_t rs[32];
-          tmem_ld_32x32b_x32(trow + cb + 32u * k, rs);
-          tmem_ld_wait();
-          float pm = -INFINITY;
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
+      }
+      // ---- pass 2: e = exp2(x - max) (exact zeros in the rows of padding) back over S, row sum ----
+      float sum = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < NPIECE; ++k) {
+        uint32_t rs[32];
+        tmem_ld_32x32b_x32(trow + scol + 32u * k, rs);
+        tmem_ld_wait();
+        float x[32];
+        scores_piece(rs, k, x);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = 32 * k + j;
-            float x = __uint_as_float(rs[j]) * sl2;
-            if (has_bias && col < L) x = fmaf(brow[col], LOG2E, x);
-            x = col < L ? x : -INFINITY;
-            rs[j] = __float_as_uint(x);
-            pm = fmaxf(pm, x);
-          }
-          const float mn = fmaxf(m, pm);
-          float acc = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc += ex2_approx(__uint_as_float(rs[j]) - mn);
-          l = l * ex2_approx(m - mn) + acc;
-          m = mn;
-          tmem_st_32x32b_x32(trow + cb + 32u * k, rs);
+        for (int j = 0; j < 32; ++j) {
+          const float e = valid ? ex2_approx(x[j] - mx) : 0.f;
+          sum += e;
+          rs[j] = __float_as_uint(e);
         }
+        tmem_st_32x32b_x32(trow + scol + 32u * k, rs);
       }
       tmem_st_wait();
-      const float inv = 1.0f / l;
-      uint32_t keepb[MAXP];
-#pragma unroll
-      for (int k = 0; k < MAXP; ++k) {
-        uint32_t kb = 0xffffffffu;
-        if (drop && k < npiece) {
-          kb = 0u;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int n = 4 * k + u;
-            uint32_t m8 = 0xffu;
-            if (valid && n * 8 < L) m8 = dropout_keep8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), p.drop_thr16);
-            kb |= m8 << (8 * u);
-          }
-        }
-        keepb[k] = kb;
+      const float inv = valid ? 1.0f / sum : 0.f;
+      const float ic = inv * p.drop_scale;
+      if (BWD) {
+        TWAIT(w_dp, mbar_wait(dp_full, (uint32_t)it & 1u, 8));
+        tcgen05_fence_after();
       }
-      if (!BWD) {
-        // ---- pass 2 (forward): P = dropout(softmax) -> bf16 block-diagonal operand ----
+      // ---- pass 3: post-dropout probabilities (packed bf16) ; backward: t = P_dropped * dP back over dP, delta ----
+      uint32_t pk[16 * NPIECE];
+      float delta = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < NPIECE; ++k) {
+        uint32_t re[32], rd[32], tmp[16];
+        tmem_ld_32x32b_x32(trow + scol + 32u * k, re);
+        if (BWD) tmem_ld_32x32b_x32(trow + DP_COL0 + 32u * k, rd);
+        tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < MAXP; ++k) {
-          if (k < npiece) {
-            uint32_t rs[32];
-            tmem_ld_32x32b_x32(trow + cb + 32u * k, rs);
-            tmem_ld_wait();
-            float pd[32];
+        for (int u = 0; u < 4; ++u) {
+          const int n = 4 * k + u;
+          uint32_t rnd[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+          if (drop && n * 8 < L) dropout_rand8(p.seed, p.offset, (uint64_t)(grow * ld8 + n), rnd);
+          float pd[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float pr = ex2_approx(__uint_as_float(rs[j]) - m) * inv;
-              pd[j] = (valid && ((keepb[k] >> j) & 1u)) ? pr * p.drop_scale : 0.f;
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint32_t word = rnd[jj >> 1];
+            const bool kept = (jj & 1) ? (word >= thr_hi) : ((word << 16) >= thr_hi);
+            pd[jj] = kept ? __uint_as_float(re[8 * u + jj]) * ic : 0.f;
+            if (BWD) {
+              const float x = valid ? pd[jj] * __uint_as_float(rd[8 * u + jj]) : 0.f;
+              rd[8 * u + jj] = __float_as_uint(x);
+              delta += x;
             }
-            if (p.probs != nullptr && valid) {
-              float* prow = p.probs + grow * (int64_t)L;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (32 * k + j < L) prow[32 * k + j] = pd[j];
-            }
-            store_piece_bf16(sP, r, (int)cb + 32 * k, pd);
           }
-        }
-      } else {
-        // ---- pass 2 (backward): p and the dropout-masked dP back into TMEM, delta = sum_j p dP ----
-        float delta = 0.f;
+          if (!BWD && p.probs != nullptr && valid) {
+            float* prow = p.probs + grow * (int64_t)L;
 #pragma unroll
-        for (int k = 0; k < MAXP; ++k) {
-          if (k < npiece) {
-            uint32_t rs[32], rd[32];
-            tmem_ld_32x32b_x32(trow + cb + 32u * k, rs);
-            tmem_ld_32x32b_x32(trow + DP_COL0 + cb + 32u * k, rd);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float pr = ex2_approx(__uint_as_float(rs[j]) - m) * inv;
-              const float d = (((keepb[k] >> j) & 1u) && (32 * k + j < L)) ? __uint_as_float(rd[j]) * p.drop_scale : 0.f;
-              delta = fmaf(pr, d, delta);
-              rs[j] = __float_as_uint(pr);
-              rd[j] = __float_as_uint(d);
-            }
-            tmem_st_32x32b_x32(trow + cb + 32u * k, rs);
-            tmem_st_32x32b_x32(trow + DP_COL0 + cb + 32u * k, rd);
+            for (int jj = 0; jj < 8; ++jj)
+              if (8 * n + jj < L) prow[8 * n + jj] = pd[jj];
           }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) tmp[4 * u + jj] = pack_bf16x2(pd[2 * jj], pd[2 * jj + 1]);
         }
+        if (BWD) tmem_st_32x32b_x32(trow + DP_COL0 + 32u * k, rd);
+        if (k == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = tmp[j];
+        } else if (k == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[16 + j] = tmp[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[32 + j] = tmp[j];
+        }
+      }
+      uint32_t dk[BWD ? 16 * NPIECE : 1];
+      if (BWD) {
         tmem_st_wait();
-        // ---- pass 3: dS = p (dP - delta) ; bias gradient ; bf16 P (post-dropout) and scale * dS operands ----
-        const bool want_db = p.dbias != nullptr;
+        // ---- pass 4: scale * dS = scale (t - p delta) packed bf16 ; bias gradient (scaled; unscaled at the flush) ----
+        const float nk = -inv * delta * p.scale;
+#pragma unroll 1
+        for (int k = 0; k < NPIECE; ++k) {
+          uint32_t re[32], rt[32], rb[32], tmp[16];
+          tmem_ld_32x32b_x32(trow + scol + 32u * k, re);
+          tmem_ld_32x32b_x32(trow + DP_COL0 + 32u * k, rt);
+          if (want_db) tmem_ld_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < MAXP; ++k) {
-          if (k < npiece) {
-            uint32_t rs[32], rd[32], rb[32];
-            tmem_ld_32x32b_x32(trow + cb + 32u * k, rs);
-            tmem_ld_32x32b_x32(trow + DP_COL0 + cb + 32u * k, rd);
-            if (want_db) tmem_ld_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
-            tmem_ld_wait();
-            float pd[32], ds[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = 32 * k + j;
-              const float pr = __uint_as_float(rs[j]);
-              float x = pr * (__uint_as_float(rd[j]) - delta);
-              x = (valid && col < L) ? x : 0.f;
-              if (want_db) rb[j] = __float_as_uint(__uint_as_float(rb[j]) + x);
-              ds[j] = x * p.scale;  // the 1/sqrt(dk) of dQ = scale dS K and dK = scale dS^T Q
-              pd[j] = (valid && ((keepb[k] >> j) & 1u)) ? pr * p.drop_scale : 0.f;
+          for (int j2 = 0; j2 < 16; ++j2) {
+            const float d0 = fmaf(__uint_as_float(re[2 * j2]), nk, __uint_as_float(rt[2 * j2]) * p.scale);
+            const float d1 = fmaf(__uint_as_float(re[2 * j2 + 1]), nk, __uint_as_float(rt[2 * j2 + 1]) * p.scale);
+            if (want_db) {
+              rb[2 * j2] = __float_as_uint(__uint_as_float(rb[2 * j2]) + d0);
+              rb[2 * j2 + 1] = __float_as_uint(__uint_as_float(rb[2 * j2 + 1]) + d1);
             }
-            if (want_db) tmem_st_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
-            store_piece_bf16(sP, r, (int)cb + 32 * k, pd);
-            store_piece_bf16(sDS, r, (int)cb + 32 * k, ds);
+            tmp[j2] = pack_bf16x2(d0, d1);
+          }
+          if (want_db) tmem_st_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
+          if (k == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dk[BWD ? j : 0] = tmp[j];
+          } else if (k == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dk[BWD ? 16 + j : 0] = tmp[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dk[BWD ? 32 + j : 0] = tmp[j];
           }
         }
-        tmem_st_wait();
+        if (want_db) tmem_st_wait();
+      }
+      if (it > 0) TWAIT(w_pe, mbar_wait(p_empty, ((uint32_t)it - 1u) & 1u, 7));  // the products of the previous tile have read P (dS)
+#pragma unroll
+      for (int k = 0; k < NPIECE; ++k) {
+        store_piece_packed(sP, r, 32 * k, pk + 16 * k);
+        if (BWD) store_piece_packed(sDS, r, 32 * k, dk + (BWD ? 16 * k : 0));
       }
       fence_proxy_async();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    if (BWD && p.dbias != nullptr) {
-      // one atomic flush of the bias gradient this CTA accumulated (the CLS row / column carries no bias)
+    if (threadIdx.x == 0)
+      TPRINT("softmax : total %lld cyc, waiting for S %lld, for dP %lld, for P / dS to be released %lld\n",
+             clock64() - t_begin, w_s, w_dp, w_pe);
+    if (want_db) {
+      const float unscale = 1.0f / p.scale;
 #pragma unroll
-      for (int k = 0; k < MAXP; ++k) {
-        if (k < npiece) {
-          uint32_t rb[32];
-          tmem_ld_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
-          tmem_ld_wait();
-          if (i >= 1 && i < L) {
-            float* drow = p.dbias + ((int64_t)h * L + i) * L;
+      for (int k = 0; k < NPIECE; ++k) {
+        uint32_t rb[32];
+        tmem_ld_32x32b_x32(trow + DB_COL0 + 32u * k, rb);
+        tmem_ld_wait();
+        if (r >= 1 && r < L) {
+          float* drow = p.dbias + ((int64_t)h * L + r) * L;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = 32 * k + j;
-              if (col >= 1 && col < L) atomicAdd(drow + col, __uint_as_float(rb[j]));
-            }
+          for (int j = 0; j < 32; ++j) {
+            const int col = 32 * k + j;
+            if (col >= 1 && col < L) atomicAdd(drow + col, __uint_as_float(rb[j]) * unscale);
           }
         }
       }
     }
-  } else {
-    // ===================== epilogue warps: accumulator chunk -> bf16 -> staging tile -> TMA store =====================
+  } else if (warp < 8 || warp >= 12) {
+    // ===================== epilogue warps: two groups (warps 4-7 and 12-15), each takes every other product and owns
+    // one staging tile, so the TMEM drain / convert / TMA store of consecutive products overlap =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
     const int q = warp & 3;
+    const int grp = warp >= 12 ? 1 : 0;
     const int r = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool leader = threadIdx.x == 6 * 32;
+    const bool leader = threadIdx.x == (grp ? 12 * 32 : 4 * 32);
+    const uint32_t stg = sStg + (uint32_t)grp * TILE_B;
     uint32_t n = 0;
-    for (int t = blockIdx.x; t < tp.tiles; t += gridDim.x) {
-      const int w0 = t * G;
+    TDECL(w_af = 0, t_begin = clock64());
+    for (int it = 0; it < n_my; ++it) {
+      const int w0 = (int)blockIdx.x + it * (int)gridDim.x;
 #pragma unroll 1
       for (int prod = 0; prod < NPROD; ++prod, ++n) {
+        if ((int)(n & 1u) != grp) continue;
         const uint32_t slot = n % NACC;
-        mbar_wait(acc_full(slot), (n / NACC) & 1u, 6);
+        TWAIT(w_af, mbar_wait(acc_full(slot), (n / NACC) & 1u, 6));
         tcgen05_fence_after();
         uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(trow + ACC_COL0 + 64u * slot, r0);
-        tmem_ld_32x32b_x32(trow + ACC_COL0 + 64u * slot + 32u, r1);
+        tmem_ld_32x32b_x32(trow + acc_col(slot), r0);
+        tmem_ld_32x32b_x32(trow + acc_col(slot) + 32u, r1);
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(slot));
-        const uint32_t stg = sStg + (n & 1u) * TILE_B;
-        if (leader) tma_wait_group_read<1>();  // the store issued two products ago no longer reads this buffer
-        named_bar_sync(1, 128);
+        if (leader) tma_wait_group_read<0>();  // this group's previous store no longer reads its staging tile
+        named_bar_sync(1 + grp, 128);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;
@@ -481,25 +623,24 @@ attn_tc_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, co
           st_shared_v4(stg + sw128(r, 4 + c), u);
         }
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + grp, 128);
         if (leader) {
           const int c = BWD ? prod / 3 : prod;
-          const int which = BWD ? prod - 3 * c : 0;  // 0: dQ (or O), 1: dK, 2: dV
-          tma_store_3d(&tm_out, stg, which * HD + h * DK + 64 * c, 0, w0);
+          const int which = BWD ? prod - 3 * c : 0;
+          tma_store_3d_hint(&tm_out, stg, which * HD + h * DK + 64 * c, 0, w0, L2_EVICT_FIRST);
           tma_commit_group();
         }
       }
     }
     if (leader) tma_wait_group<0>();
+    if (leader) TPRINT("epilogue%d: total %lld cyc, waiting for an accumulator %lld\n", grp, clock64() - t_begin, w_af);
   }
 
-  // ---------------- teardown ----------------
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
-
 
 // ==========================================================================================================
 // Windows of L <= 64 tokens: M = 64 products, two per tile, software-pipelined across tiles.
@@ -535,7 +676,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
 
   Params p = tp.p;
   p.offset += rng_step();
-  const int NS = tp.n_stages;
+  const int NS = tp.n_stages, NSA = tp.n_stages_a, NSB = tp.n_stages_b;
   const int L = p.L;
   const int h = blockIdx.y;
   const int HD = p.H * DK;
@@ -549,13 +690,18 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
   const uint32_t sStg = BWD ? sDS + 2 * SUB_B : sDS;
   const uint32_t sBias = sStg + 2 * TILE_B;
   const uint32_t sBar = sBias + tp.bias_bytes;
-  auto full_bar = [&](int s) { return sBar + 8u * s; };
-  auto empty_bar = [&](int s) { return sBar + 8u * (MAX_STAGES + s); };
-  auto s_full = [&](uint32_t b) { return sBar + 8u * (2 * MAX_STAGES + b); };
-  const uint32_t p_full = sBar + 8u * (2 * MAX_STAGES + 2), p_empty = p_full + 8u;
-  auto acc_full = [&](int a) { return sBar + 8u * (2 * MAX_STAGES + 4 + a); };
-  auto acc_empty = [&](int a) { return sBar + 8u * (2 * MAX_STAGES + 8 + a); };
-  const uint32_t tmem_slot = sBar + 8u * (2 * MAX_STAGES + 12);
+  // two operand rings with their own producer and issuer thread each: A = operands of the score products, B = operands of
+  // the chunk products; ring B's stages follow ring A's in shared memory
+  const uint32_t sRingB = sRing + (uint32_t)NSA * TILE_B;
+  auto full_a = [&](int s) { return sBar + 8u * s; };
+  auto empty_a = [&](int s) { return sBar + 8u * (MAX_STAGES + s); };
+  auto full_b = [&](int s) { return sBar + 8u * (2 * MAX_STAGES + s); };
+  auto empty_b = [&](int s) { return sBar + 8u * (3 * MAX_STAGES + s); };
+  auto s_full = [&](uint32_t b) { return sBar + 8u * (4 * MAX_STAGES + b); };
+  const uint32_t p_full = sBar + 8u * (4 * MAX_STAGES + 2), p_empty = p_full + 8u;
+  auto acc_full = [&](int a) { return sBar + 8u * (4 * MAX_STAGES + 4 + a); };
+  auto acc_empty = [&](int a) { return sBar + 8u * (4 * MAX_STAGES + 8 + a); };
+  const uint32_t tmem_slot = sBar + 8u * (4 * MAX_STAGES + 12);
   float* bias_s = reinterpret_cast<float*>(smem + (sBias - smem_u32(smem)));
 
   // ---------------- start-up ----------------
@@ -563,9 +709,13 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_out);
     if (BWD) tma_prefetch_desc(&tm_do);
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < NSA; ++s) {
+      mbar_init(full_a(s), 1);
+      mbar_init(empty_a(s), 1);
+    }
+    for (int s = 0; s < NSB; ++s) {
+      mbar_init(full_b(s), 1);
+      mbar_init(empty_b(s), 1);
     }
     mbar_init(s_full(0), 1);
     mbar_init(s_full(1), 1);
@@ -602,54 +752,58 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
   }
-  if (warp == 8) {
-    // ===================== TMA producer =====================
+  if (warp == 8 || warp == 11) {
+    // ===================== TMA producers: warp 8 feeds ring A, warp 11 ring B, each in its issuer's order =====================
     if (lane == 0) {
+      const bool ring_a = warp == 8;
+      const int n_s = ring_a ? NSA : NSB;
+      const uint32_t base = ring_a ? sRing : sRingB;
       int s = 0;
       uint32_t ph = 0;
       auto load = [&](const CUtensorMap* tm, int col, int w0, uint64_t policy) {
-        mbar_wait(empty_bar(s), ph ^ 1u, 1);
-        mbar_arrive_expect_tx(full_bar(s), TILE_B);
-        tma_load_3d_hint(sRing + (uint32_t)s * TILE_B, tm, full_bar(s), col, 0, w0, policy);
-        if (++s == NS) { s = 0; ph ^= 1u; }
+        const uint32_t fb = ring_a ? full_a(s) : full_b(s);
+        mbar_wait(ring_a ? empty_a(s) : empty_b(s), ph ^ 1u, 1);
+        mbar_arrive_expect_tx(fb, TILE_B);
+        tma_load_3d_hint(base + (uint32_t)s * TILE_B, tm, fb, col, 0, w0, policy);
+        if (++s == n_s) { s = 0; ph ^= 1u; }
       };
       // backward: q, k, dO are read again by the chunk products of the same tile -> keep them in L2 until then;
       // everything that is read for the last time leaves L2 first
       const uint64_t pol_again = BWD ? L2_EVICT_LAST : L2_EVICT_FIRST, pol_once = L2_EVICT_FIRST;
       const int cq = h * DK, ck = HD + h * DK, cv = 2 * HD + h * DK;
-      // load order = the order the MMA warp consumes: A(0), A(1), then per tile and 64-column chunk c the operands of
-      // the chunk products of tile `it` followed by the score operands of tile `it + 2`
-      auto load_a = [&](int it, int c) {
-        const int w0 = ((int)blockIdx.x + it * (int)gridDim.x) * G;
-        load(&tm_qkv, cq + 64 * c, w0, pol_again);
-        load(&tm_qkv, ck + 64 * c, w0, pol_again);
-        if (BWD) {
-          load(&tm_do, cq + 64 * c, w0, pol_again);
-          load(&tm_qkv, cv + 64 * c, w0, pol_once);
-        }
-      };
-      auto load_b = [&](int it, int c) {
-        const int w0 = ((int)blockIdx.x + it * (int)gridDim.x) * G;
-        if (BWD) {
-          load(&tm_qkv, ck + 64 * c, w0, pol_once);
-          load(&tm_qkv, cq + 64 * c, w0, pol_once);
-          load(&tm_do, cq + 64 * c, w0, pol_once);
-        } else {
-          load(&tm_qkv, cv + 64 * c, w0, pol_once);
-        }
-      };
-      for (int it = 0; it < 2 && it < n_my; ++it)
-        for (int c = 0; c < NC; ++c) load_a(it, c);
-      for (int it = 0; it < n_my; ++it) {
-        for (int c = 0; c < NC; ++c) {
-          load_b(it, c);
-          if (it + 2 < n_my) load_a(it + 2, c);
-        }
+      auto w0_of = [&](int it) { return ((int)blockIdx.x + it * (int)gridDim.x) * G; };
+      if (ring_a) {
+        auto load_a = [&](int it) {
+          for (int c = 0; c < NC; ++c) {
+            load(&tm_qkv, cq + 64 * c, w0_of(it), pol_again);
+            load(&tm_qkv, ck + 64 * c, w0_of(it), pol_again);
+            if (BWD) {
+              load(&tm_do, cq + 64 * c, w0_of(it), pol_again);
+              load(&tm_qkv, cv + 64 * c, w0_of(it), pol_once);
+            }
+          }
+        };
+        for (int it = 0; it < n_my; ++it) load_a(it);
+      } else {
+        for (int it = 0; it < n_my; ++it)
+          for (int c = 0; c < NC; ++c) {
+            if (BWD) {
+              load(&tm_qkv, ck + 64 * c, w0_of(it), pol_once);
+              load(&tm_qkv, cq + 64 * c, w0_of(it), pol_once);
+              load(&tm_do, cq + 64 * c, w0_of(it), pol_once);
+            } else {
+              load(&tm_qkv, cv + 64 * c, w0_of(it), pol_once);
+            }
+          }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers (see attn_tc128_kernel): warp 9 score products from ring A, warp 10 chunk
+    // products from ring B =====================
     if (lane == 0) {
+      const bool do_a = warp == 9;
+      const int n_s = do_a ? NSA : NSB;
+      const uint32_t base = do_a ? sRing : sRingB;
       const uint32_t M64 = (64u >> 4) << 24, M128 = (128u >> 4) << 24;
       const uint32_t id_s = (idesc_bf16_m128(64u, false, false) & ~M128) | M64;
       const uint32_t id_pk = (idesc_bf16_m128(64u, false, true) & ~M128) | M64;
@@ -657,10 +811,10 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       int s = 0;
       uint32_t ph = 0, nacc = 0;
       auto acquire = [&]() -> uint32_t {
-        mbar_wait(full_bar(s), ph, 2);
-        return sRing + (uint32_t)s * TILE_B;
+        mbar_wait(do_a ? full_a(s) : full_b(s), ph, 2);
+        return base + (uint32_t)s * TILE_B;
       };
-      auto advance = [&]() { if (++s == NS) { s = 0; ph ^= 1u; } };
+      auto advance = [&]() { if (++s == n_s) { s = 0; ph ^= 1u; } };
       // per sub-tile g: acc_g (64 x 64) (+)= A_tile[g] (64 x 64) * B_tile[g]^T, two consecutive ring stages
       auto score_product = [&](uint32_t col, bool first) {
         const uint32_t a = acquire();
@@ -675,8 +829,8 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2u * k, db + 2u * k, id_s, (!first || k > 0) ? 1u : 0u);
         }
-        umma_commit(empty_bar(sa));
-        umma_commit(empty_bar(s));
+        umma_commit(empty_a(sa));
+        umma_commit(empty_a(s));
         advance();
       };
       // per sub-tile g: slot_g (64 x 64) = A_g (P or dS, [64 x 64], K- or MN-major) * ring tile rows of g (MN-major B)
@@ -694,33 +848,41 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
           for (int j = 0; j < 4; ++j)
             umma_bf16(d, da + (a_mn ? 128u : 2u) * j, db + 128u * j, a_mn ? id_ptk : id_pk, j > 0 ? 1u : 0u);
         }
-        umma_commit(empty_bar(s));
+        umma_commit(empty_b(s));
         advance();
         umma_commit(acc_full(slot));
         ++nacc;
       };
-      // score products of chunk c of tile `it` (buffer it & 1); the last chunk publishes the buffer to the softmax warps
-      auto phase_a = [&](int it, int c) {
-        const uint32_t b = (uint32_t)it & 1u;
-        score_product(64u * b, c == 0);
-        if (BWD) score_product(DP_COL0 + 64u * b, c == 0);
-        if (c == NC - 1) umma_commit(s_full(b));
-      };
-      for (int it = 0; it < 2 && it < n_my; ++it)
-        for (int c = 0; c < NC; ++c) phase_a(it, c);
-      for (int it = 0; it < n_my; ++it) {
-        mbar_wait(p_full, (uint32_t)it & 1u, 4);  // also: the softmax has finished reading S / dP buffer it & 1
-        tcgen05_fence_after();
-        for (int c = 0; c < NC; ++c) {
-          if (BWD) {
-            chunk_product(sDS, false);  // dQ_c = dS K_c
-            chunk_product(sDS, true);   // dK_c = dS^T Q_c
-            chunk_product(sP, true);    // dV_c = P^T dO_c
-          } else {
-            chunk_product(sP, false);   // O_c = P V_c
+      if (do_a) {
+        // score products of tile `it` into buffer it & 1, published to the softmax warps by the last chunk
+        auto phase_a = [&](int it) {
+          const uint32_t b = (uint32_t)it & 1u;
+          for (int c = 0; c < NC; ++c) {
+            score_product(64u * b, c == 0);
+            if (BWD) score_product(DP_COL0 + 64u * b, c == 0);
           }
-          if (c == NC - 1) umma_commit(p_empty);  // P / dS may be overwritten once these products retire
-          if (it + 2 < n_my) phase_a(it + 2, c);  // HBM-bound score operands interleave with the L2-resident re-reads
+          umma_commit(s_full(b));
+        };
+        for (int it = 0; it < 2 && it < n_my; ++it) phase_a(it);
+        for (int it = 0; it + 2 < n_my; ++it) {
+          mbar_wait(p_full, (uint32_t)it & 1u, 4);  // the softmax has finished reading S / dP buffer it & 1
+          tcgen05_fence_after();
+          phase_a(it + 2);
+        }
+      } else {
+        for (int it = 0; it < n_my; ++it) {
+          mbar_wait(p_full, (uint32_t)it & 1u, 4);  // P / dS of tile `it` written
+          tcgen05_fence_after();
+          for (int c = 0; c < NC; ++c) {
+            if (BWD) {
+              chunk_product(sDS, false);  // dQ_c = dS K_c
+              chunk_product(sDS, true);   // dK_c = dS^T Q_c
+              chunk_product(sP, true);    // dV_c = P^T dO_c
+            } else {
+              chunk_product(sP, false);   // O_c = P V_c
+            }
+          }
+          umma_commit(p_empty);  // P / dS may be overwritten once these products retire
         }
       }
     }
@@ -955,7 +1117,7 @@ static int make_tmap3d(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t L
 typedef void (*KernelFn)(const TcParams, const CUtensorMap, const CUtensorMap, const CUtensorMap);
 template <int LP, int DK, bool BWD>
 static KernelFn kernel_for() {
-  if constexpr (LP == 128) return attn_tc_kernel<128, DK, BWD>;
+  if constexpr (LP == 128) return attn_tc128_kernel<DK, BWD>;
   else return attn_tc64_kernel<LP, DK, BWD>;
 }
 
@@ -968,17 +1130,22 @@ static int launch(const Params& p, cudaStream_t stream) {
   tp.tiles = (int)((p.W + G - 1) / G);
   tp.nkeys = (G > 1) ? 128 : ((p.L + 15) / 16) * 16;
   tp.ks_tok = (G > 1) ? 8 : tp.nkeys / 16;
-  tp.npiece = (G > 1) ? LP / 32 : (tp.nkeys + 31) / 32;
-  if (G > 1) {  // sub-tile kernel: always staged, LP columns per row (padding columns hold -inf)
+  tp.npiece = (G > 1) ? LP / 32 : 3;
+  uint32_t stage_b, fixed;
+  if (G > 1) {
+    // sub-tile kernel: bias always staged (fp32, LP columns per row, padding columns hold -inf); P / dS 2 x [64 x 64]
     tp.bias_pitch = LP + 1;
     tp.bias_bytes = (uint32_t)(((size_t)p.L * tp.bias_pitch * 4 + 15) / 16 * 16);
+    stage_b = TILE_B;
+    fixed = 1024u + (BWD ? 4u : 2u) * 8192u + 2u * TILE_B + tp.bias_bytes + BAR_BYTES;
   } else {
-    tp.bias_pitch = p.L | 1;
-    tp.bias_bytes = p.bias != nullptr ? (uint32_t)(((size_t)p.L * tp.bias_pitch * 4 + 15) / 16 * 16) : 0u;
+    // one window per tile: stages of nkeys rows, bias as bf16 pairs (49 words per row)
+    tp.bias_pitch = 49;
+    tp.bias_bytes = (uint32_t)(((size_t)p.L * 49 * 4 + 15) / 16 * 16);
+    stage_b = (uint32_t)tp.nkeys * 128u;
+    fixed = 1024u + (BWD ? 4u : 2u) * PANEL_B + 2u * TILE_B + tp.bias_bytes + BAR_BYTES;
   }
-  constexpr uint32_t OPERAND_B = (G > 1) ? 8192u : PANEL_B;  // P (and dS): 2 x [64 x 64] or 2 panels of [128 x 64]
-  const uint32_t fixed = 1024u + (BWD ? 4u : 2u) * OPERAND_B + 2u * TILE_B + tp.bias_bytes + BAR_BYTES;
-  int ns = (int)((SMEM_LIMIT - fixed) / TILE_B);
+  int ns = (int)((SMEM_LIMIT - fixed) / stage_b);
   if (ns > MAX_STAGES) ns = MAX_STAGES;
   {
     static const int cap = [] {  // LSTC_ATTN_STAGES=<n>: cap the ring depth (experiments on latency hiding)
@@ -987,22 +1154,40 @@ static int launch(const Params& p, cudaStream_t stream) {
     }();
     if (cap >= 3 && ns > cap) ns = cap;
   }
-  if (ns < 3) {
+  if (ns < 4) {
     set_last_error("attention: no shared memory left for the operand ring (L=%d)", p.L);
     return LSTC_ERR_UNSUPPORTED;
   }
+  // ring B (chunk-product operands): forward = v (first read, HBM-bound, a third of the loads); backward = k, q, dO
+  // re-read through L2 (short latency): three stages keep its issuer fed
+  int nsb = BWD ? 3 : (ns + 2) / 3;
+  {
+    static const int nsb_env = [] {  // LSTC_ATTN_STAGES_B=<n>: depth of ring B (experiments)
+      const char* e = getenv("LSTC_ATTN_STAGES_B");
+      return e != nullptr ? atoi(e) : 0;
+    }();
+    if (nsb_env > 0) nsb = nsb_env;
+  }
+  if (nsb < 2) nsb = 2;
+  if (ns - nsb < 2) {
+    set_last_error("attention: no shared memory left for the operand rings (L=%d)", p.L);
+    return LSTC_ERR_UNSUPPORTED;
+  }
   tp.n_stages = ns;
-  const uint32_t smem = fixed + (uint32_t)ns * TILE_B;
+  tp.n_stages_a = ns - nsb;
+  tp.n_stages_b = nsb;
+  const uint32_t smem = fixed + (uint32_t)ns * stage_b;
+  const int box_rows = (G > 1) ? LP : tp.nkeys;
   const int HD = p.H * DK;
   CUtensorMap tq, td, to;
   memset(&td, 0, sizeof(td));
-  int rc = make_tmap3d(&tq, p.qkv, 3 * (int64_t)HD, p.L, p.W, p.ld, LP, G);
+  int rc = make_tmap3d(&tq, p.qkv, 3 * (int64_t)HD, p.L, p.W, p.ld, box_rows, G);
   if (rc != LSTC_OK) return rc;
   if (BWD) {
-    rc = make_tmap3d(&td, p.dout, HD, p.L, p.W, p.ld_dout, LP, G);
+    rc = make_tmap3d(&td, p.dout, HD, p.L, p.W, p.ld_dout, box_rows, G);
     if (rc != LSTC_OK) return rc;
   }
-  rc = make_tmap3d(&to, p.out, (BWD ? 3 : 1) * (int64_t)HD, p.L, p.W, p.ld_out, LP, G);
+  rc = make_tmap3d(&to, p.out, (BWD ? 3 : 1) * (int64_t)HD, p.L, p.W, p.ld_out, box_rows, G);
   if (rc != LSTC_OK) return rc;
   auto kern = kernel_for<LP, DK, BWD>();
   static bool attr_set[64] = {false};  // per instantiation and device; idempotent
@@ -1015,7 +1200,7 @@ static int launch(const Params& p, cudaStream_t stream) {
   int gx = num_sms() / p.H;
   if (gx < 1) gx = 1;
   if (gx > tp.tiles) gx = tp.tiles;
-  kern<<<dim3((unsigned)gx, (unsigned)p.H), LP == 128 ? NUM_THREADS : NUM_THREADS64, smem, stream>>>(tp, tq, td, to);
+  kern<<<dim3((unsigned)gx, (unsigned)p.H), LP == 128 ? NUM_THREADS128 : NUM_THREADS64, smem, stream>>>(tp, tq, td, to);
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }

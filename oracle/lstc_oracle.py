@@ -50,10 +50,21 @@ class bf16_rounding:
         _BF16_MODE = self.prev
 
 
-def _r(x: Tensor) -> Tensor:
+def _round_bf16(g: Tensor) -> Tensor:
+    return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _r(x: Tensor, grad: bool = True) -> Tensor:
+    """bf16-faithful mode: x rounded to bf16 (straight-through).  `grad`: the gradient arriving at this tensor in the
+    backward is rounded to bf16 as well - wherever the CUDA path keeps an ACTIVATION in bf16 it also hands the
+    gradient with respect to it to the next kernel in bf16 (dX, dqkv, dO, the LayerNorm input gradients, dH).  Weights
+    and the attention probabilities are forward-only: their gradients stay fp32 (dW, and dP in TMEM)."""
     if not _BF16_MODE:
         return x
-    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+    y = x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+    if grad and y.requires_grad:
+        y.register_hook(_round_bf16)
+    return y
 
 
 @dataclass
@@ -156,9 +167,9 @@ def mha_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, cfg: EncoderConfi
     Returns (out [W,L,D], attn [W,H,L,L] post-dropout, v [W,H,L,dv])."""
     W, L, _ = x.shape
     H, dk, dv = cfg.n_head, cfg.d_k, cfg.d_v
-    q = _r(x @ _r(sd[prefix + "w_qs.weight"]).t()).reshape(W, L, H, dk).permute(0, 2, 1, 3)
-    k = _r(x @ _r(sd[prefix + "w_ks.weight"]).t()).reshape(W, L, H, dk).permute(0, 2, 1, 3)
-    v = _r(x @ _r(sd[prefix + "w_vs.weight"]).t()).reshape(W, L, H, dv).permute(0, 2, 1, 3)
+    q = _r(x @ _r(sd[prefix + "w_qs.weight"], False).t()).reshape(W, L, H, dk).permute(0, 2, 1, 3)
+    k = _r(x @ _r(sd[prefix + "w_ks.weight"], False).t()).reshape(W, L, H, dk).permute(0, 2, 1, 3)
+    v = _r(x @ _r(sd[prefix + "w_vs.weight"], False).t()).reshape(W, L, H, dv).permute(0, 2, 1, 3)
     s = (q / (dk ** 0.5)) @ k.transpose(2, 3)  # :103 — scale applied to q before the product
     if cfg.relative_pe:  # :107-111
         b = relative_bias(sd[prefix + "relative_position_bias_table"], sd[prefix + "relative_position_index"], L - 1)
@@ -172,11 +183,13 @@ def mha_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, cfg: EncoderConfi
         pad = torch.cat([torch.zeros(H, 1, L, dtype=s.dtype),
                          torch.cat([torch.zeros(H, L - 1, 1, dtype=s.dtype), b], dim=2)], dim=1)
         s = s + pad.unsqueeze(0)
+    if _BF16_MODE and s.requires_grad:
+        s.register_hook(_round_bf16)  # the CUDA backward stores (scale * dS) as a bf16 operand of dQ / dK
     attn = torch.softmax(s, dim=-1)
     if masks is not None:
         attn = _apply_mask(attn, masks.attn.get(layer), masks.attn_p)  # :119
-    o = _r(_r(attn) @ v).permute(0, 2, 1, 3).reshape(W, L, H * dv)  # :120-122
-    o = o @ _r(sd[prefix + "fc.weight"]).t()
+    o = _r(_r(attn, False) @ v).permute(0, 2, 1, 3).reshape(W, L, H * dv)  # :120-122
+    o = o @ _r(sd[prefix + "fc.weight"], False).t()
     if masks is not None:
         o = _apply_mask(o, masks.fc.get(layer), masks.fc_p)  # :123
     o = _r(o + x)  # :124
@@ -188,8 +201,8 @@ def mha_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, cfg: EncoderConfi
 def ffn_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, cfg: EncoderConfig, layer: int = 0,
                 masks: Optional[DropoutMasks] = None, last: bool = False) -> Tensor:
     """models/FFN.py:14-22.  `last`: the encoder's final block (its LayerNorm output stays fp32 in the CUDA path)."""
-    h = _r(torch.relu(x @ _r(sd[prefix + "w_1.weight"]).t() + sd[prefix + "w_1.bias"]))
-    y = h @ _r(sd[prefix + "w_2.weight"]).t() + sd[prefix + "w_2.bias"]
+    h = _r(torch.relu(x @ _r(sd[prefix + "w_1.weight"], False).t() + sd[prefix + "w_1.bias"]))
+    y = h @ _r(sd[prefix + "w_2.weight"], False).t() + sd[prefix + "w_2.bias"]
     if masks is not None:
         y = _apply_mask(y, masks.ffn.get(layer), masks.ffn_p)
     y = _r(y + x)
@@ -230,7 +243,7 @@ def head_forward(sd: Dict[str, Tensor], x: Tensor, kind: str, masks: Optional[Tu
     """Classifier (models/Classifier.py:8-23, kind='classifier', softmax over 2 classes) or Regressor
     (models/Regressor.py:7-20, kind='regressor', sigmoid).  ReLU only after the first Linear."""
     x = _r(x.reshape(-1, x.shape[-1]))
-    h = torch.relu(x @ _r(sd[f"{kind}.0.weight"]).t() + sd[f"{kind}.0.bias"])
+    h = torch.relu(x @ _r(sd[f"{kind}.0.weight"], False).t() + sd[f"{kind}.0.bias"])
     if masks is not None:
         h = _apply_mask(h, masks[0], p)
     h = _r(h)
