@@ -289,7 +289,8 @@ def run_extras(args, wl, step, dev, world, rank, pg, B, steps, sync_all):
     return out
 
 
-def auc_delta_vs_oracle(wl, dev, train_steps: int = 12, test_windows: int = 320):
+def auc_delta_vs_oracle(wl, dev, train_steps: int = 8, test_windows: int = 640, lr_head: float = 2e-5,
+                        lr_encoder: float = 1e-6):
     """ROC-AUC delta at the headline width (BASELINE metric, second half): an LTN + Classifier at the workload's full
     width is trained briefly on a synthetic split whose abnormal windows carry a feature bump, then a fixed test split
     is scored by the CUDA path (eval mode) and by the CPU oracle with the same weights; AUCs by sklearn
@@ -316,7 +317,10 @@ def auc_delta_vs_oracle(wl, dev, train_steps: int = 12, test_windows: int = 320)
         x[is_anom] = xa
         return x, is_anom
 
-    step = TrainStep(wl, dev, seed=3, train_mode=True, optimizer=True)
+    # Adagrad's first steps move EVERY weight by ~lr in the gradient's direction: at the scripts' rates (1e-4 / 1e-2) the
+    # softmax saturates on this synthetic split within a few steps (scores collapse to 0 / 1), so the brief training
+    # runs at smaller rates; what is checked is the DELTA between the two paths on non-degenerate, informative scores
+    step = TrainStep(wl, dev, seed=3, train_mode=True, optimizer=True, lr_head=lr_head, lr_encoder=lr_encoder)
     for _ in range(train_steps):
         x, anom = batch(Bt * P, Bt * P, 0.3)
         pseudo = anom[Bt * P:].float().view(Bt, P).repeat_interleave(T, dim=1)  # per-clip labels of the abnormal bags
@@ -337,6 +341,7 @@ def auc_delta_vs_oracle(wl, dev, train_steps: int = 12, test_windows: int = 320)
     y = anom.numpy().astype(np.int32)
     a_gpu, a_cpu = roc_auc_score(y, s_gpu.numpy()), roc_auc_score(y, s_cpu.numpy())
     return {"value": abs(a_gpu - a_cpu), "auc_cuda": a_gpu, "auc_oracle_fp32": a_cpu, "bound": 1e-3,
+            "score_std": s_cpu.std().item(),
             "score_max_abs_diff": (s_gpu - s_cpu).abs().max().item(), "windows": int(x.shape[0]),
             "d_model": wl.d_model, "train_steps": train_steps,
             "what": "window-level ROC-AUC of the CUDA path vs the fp32 CPU oracle with the same briefly trained weights on "

@@ -415,15 +415,17 @@ def test_patch_embedding_class(M, learned, dtype):
     tok = pe.cls_token.detach().clone().requires_grad_(True) if learned else None
     cls = tok.expand(W, -1, -1) if learned else torch.mean(xr, dim=1, keepdim=True)
     ref = torch.cat([cls, xr], dim=1)
-    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    # the kernel's output is a bf16 token matrix (the activation format of the whole encoder, DESIGN.md "Known
+    # deviations"); fp32 callers get it widened back to fp32, i.e. rounded once to bf16
+    tol = 1e-2
     assert torch.allclose(out.float(), ref, rtol=tol, atol=tol)
-    assert torch.equal(out[:, 1:].float(), x.detach().float())   # the tokens themselves pass through untouched
+    assert torch.equal(out[:, 1:].float(), x.detach().to(torch.bfloat16).float())   # tokens pass through (as bf16)
     g = torch.randn(W, L0 + 1, D, device="cuda")
     out.float().backward(g)
     ref.backward(g)
-    assert torch.allclose(x.grad.float(), xr.grad, rtol=tol, atol=tol)
-    if learned:
-        assert torch.allclose(pe.cls_token.grad, tok.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(x.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
+    if learned:  # the gradient reaches the kernel as bf16 (it belongs to a bf16 activation): one rounding per term
+        assert torch.allclose(pe.cls_token.grad, tok.grad, rtol=2e-2, atol=2e-2)
 
 
 def test_mil_loss_flat_column_form_of_spatio_MIL_CE(L):
@@ -447,5 +449,13 @@ def test_mil_loss_flat_column_form_of_spatio_MIL_CE(L):
     loss.backward()
     ref.backward()
     assert torch.allclose(y.grad, yr.grad, rtol=1e-5, atol=1e-7)
-    # the quirk itself: rows 0..B-1 get no sparsity gradient, row B (still a NORMAL clip) does
-    assert (yr.grad[B:, 0] >= 0.01 / (2 * B * P * T - B) - 1e-9).all()
+    # the quirk itself: rows 0..B-1 get no sparsity gradient, rows B.. (still NORMAL clips up to row B*P*T) do
+    n = 2 * B * P * T
+    part_of_max = torch.zeros(n, dtype=torch.bool, device="cuda")
+    arg = torch.max(torch.mean(yr.detach().view([B * 2, P, T]), dim=-1), dim=-1)[1]          # selected part per bag
+    for bag in range(2 * B):
+        beg = (bag * P + int(arg[bag])) * T
+        part_of_max[beg:beg + T] = True
+    plain = ~part_of_max
+    assert torch.all(y.grad[:B, 0][plain[:B]] == 0)
+    assert torch.allclose(y.grad[B:, 0][plain[B:]], torch.full_like(y.grad[B:, 0][plain[B:]], 0.01 / (n - B)), rtol=1e-5)
