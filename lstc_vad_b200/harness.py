@@ -298,9 +298,11 @@ class _InjectGrad(torch.autograd.Function):
 # Train/temporal_transformer_shanghaitech.py:76-78)
 # --------------------------------------------------------------------------------------------------
 class BucketedGradReducer:
-    """Two buckets per EncoderLayer (FFN, attention) + one for everything else, reduced in reverse layer order as
-    soon as the last gradient of the bucket has been accumulated.  The bucket plan is static and only contains parameters
-    that receive gradients (LayerNorms switched off by the model flags never do — SURVEY.md §8)."""
+    """SUM all-reduce of the parameter gradients over the data-parallel ranks through flat bf16 (or fp32) buckets: one
+    multi-tensor pack launch, one NCCL all-reduce, one unpack launch per bucket.  Default plan: a single bucket reduced
+    after backward; LSTC_DP_BUCKETS=layer gives two buckets per EncoderLayer (FFN, attention) + one for everything
+    else, which LSTC_DP_REDUCE=overlap launches in reverse layer order from the backward hooks.  The plan is static and
+    only contains parameters that receive gradients (LayerNorms switched off by the model flags never do - SURVEY §8)."""
 
     def __init__(self, modules: Sequence[torch.nn.Module], process_group, comm_stream: Optional[torch.cuda.Stream] = None,
                  grad_dtype: Optional[str] = None):
@@ -320,14 +322,25 @@ class BucketedGradReducer:
         self.stream = comm_stream or torch.cuda.Stream()
         self._active = False
         self._skip: set = set()
-        # "overlap": launch a bucket's all-reduce as soon as its last gradient lands (default);
-        # "tail": launch all buckets after backward (no SM contention between NCCL and the persistent GEMMs)
-        self.mode = os.environ.get("LSTC_DP_REDUCE", "overlap")
+        # "tail" (default): launch the bucket(s) after backward (no SM contention between NCCL and the persistent GEMMs);
+        # "overlap": launch a bucket's all-reduce from the backward hooks as soon as its last gradient lands
+        self.mode = os.environ.get("LSTC_DP_REDUCE", "tail")
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
                 p.register_post_accumulate_grad_hook(self._make_hook(bi))
 
     def _plan(self, modules):
+        if os.environ.get("LSTC_DP_BUCKETS", "single") == "single":
+            # default: ONE flat bucket for the whole model (203 MB of bf16 for the LTN), reduced right after backward
+            # (LSTC_DP_REDUCE=tail): a single large all-reduce runs at NVLink / NVSwitch bus bandwidth, where several
+            # ~30 MB ones pay launch latency each, and NCCL's CTAs do not fight the persistent one-CTA-per-SM GEMMs of
+            # backward for SMs.  Measured on 8 B200 (bench.py, CUDA graph, 20 steps): 30.70 ms / step against 31.07 ms
+            # for per-layer buckets launched from the backward hooks (LSTC_DP_BUCKETS=layer LSTC_DP_REDUCE=overlap)
+            # and 31.11 ms for per-layer buckets launched after backward.
+            ps = [p for m in modules for p in m.parameters() if p.requires_grad]
+            if ps:
+                self.buckets.append(ps)
+            return
         rest = []
         for m in modules:
             stack = getattr(m, "layer_stack", None)

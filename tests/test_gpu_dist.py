@@ -23,6 +23,8 @@ def _global_batch(wl, device):
 
 def _worker(rank, world, port, out, grad_dtype):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if grad_dtype == "fp32":  # also covers the per-layer buckets launched from the backward hooks
+        os.environ.update(LSTC_DP_BUCKETS="layer", LSTC_DP_REDUCE="overlap")
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
