@@ -198,7 +198,7 @@ attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv,
     mbar_init(s_full(0), 1);
     mbar_init(s_full(1), 1);
     mbar_init(p_full, 4);
-    mbar_init(p_empty, 1);
+    mbar_init(p_empty, 2);  // one commit per chunk-product issuer
     mbar_init(dp_full, 1);
     for (int a = 0; a < NACC; ++a) {
       mbar_init(acc_full(a), 1);
@@ -236,62 +236,47 @@ attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv,
   if (warp >= 8 && warp < 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
   }
-  if (warp == 8 || warp == 11) {
-    // ===================== TMA producers: warp 8 feeds ring A, warp 11 ring B, each in its issuer's order =====================
+  if (warp == 8) {
+    // ===================== TMA producer: ONE thread feeds both rings, each in its consumers' order; it polls the two
+    // "stage free" barriers so that a full ring never holds up the other one =====================
     if (lane == 0) {
-      const bool ring_a = warp == 8;
-      const int n_s = ring_a ? NSA : NSB;
-      const uint32_t base = ring_a ? sRing : sRingB;
-      int s = 0;
-      uint32_t ph = 0;
-      TDECL(w_empty = 0, t_begin = clock64());
-      auto load = [&](const CUtensorMap* tm, int col, int w0, uint64_t policy) {
-        const uint32_t fb = ring_a ? full_a(s) : full_b(s);
-        TWAIT(w_empty, mbar_wait(ring_a ? empty_a(s) : empty_b(s), ph ^ 1u, 1));
-        mbar_arrive_expect_tx(fb, STAGE_B);
-        tma_load_3d_hint(base + (uint32_t)s * STAGE_B, tm, fb, col, 0, w0, policy);
-        if (++s == n_s) { s = 0; ph ^= 1u; }
-      };
       const uint64_t pol_again = BWD ? L2_EVICT_LAST : L2_EVICT_FIRST, pol_once = L2_EVICT_FIRST;
+      // backward: q, k, dO are read again by the chunk products of the same tile -> keep them in L2 until then;
+      // everything that is read for the last time leaves L2 first
       const int cq = h * DK, ck = HD + h * DK, cv = 2 * HD + h * DK;
-      auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
-      if (ring_a) {
-        auto load_s = [&](int it, int c) {
-          load(&tm_qkv, cq + 64 * c, tile_of(it), pol_again);
-          load(&tm_qkv, ck + 64 * c, tile_of(it), pol_again);
-        };
-        auto load_dp = [&](int it, int c) {
-          load(&tm_do, cq + 64 * c, tile_of(it), pol_again);
-          load(&tm_qkv, cv + 64 * c, tile_of(it), pol_once);
-        };
-        if (n_my > 0) {
-          for (int c = 0; c < NC; ++c) load_s(0, c);
-          if (BWD)
-            for (int c = 0; c < NC; ++c) load_dp(0, c);
+      const int na = n_my * (BWD ? 4 * NC : 2 * NC), nb = n_my * (BWD ? 3 * NC : NC);
+      int ia = 0, ib = 0, sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      TDECL(t_begin = clock64());
+      while (ia < na || ib < nb) {
+        if (ia < na && mbar_try_wait(empty_a(sa), pha ^ 1u)) {
+          const int per = BWD ? 4 * NC : 2 * NC;          // stages of ring A per tile: S(t) then dP(t)
+          const int it = ia / per, j = ia - it * per;
+          const bool dp = j >= 2 * NC;
+          const int c = (dp ? j - 2 * NC : j) >> 1, second = j & 1;
+          const CUtensorMap* tm = (dp && !second) ? &tm_do : &tm_qkv;
+          const int col = dp ? (second ? cv : cq) : (second ? ck : cq);
+          const uint64_t pol = (dp && second) ? pol_once : pol_again;
+          mbar_arrive_expect_tx(full_a(sa), STAGE_B);
+          tma_load_3d_hint(sRing + (uint32_t)sa * STAGE_B, tm, full_a(sa), col + 64 * c, 0, ((int)blockIdx.x + it * (int)gridDim.x), pol);
+          ++ia;
+          if (++sa == NSA) { sa = 0; pha ^= 1u; }
         }
-        if (n_my > 1)
-          for (int c = 0; c < NC; ++c) load_s(1, c);
-        for (int it = 0; it < n_my; ++it) {
-          if (BWD && it + 1 < n_my)
-            for (int c = 0; c < NC; ++c) load_dp(it + 1, c);
-          if (it + 2 < n_my)
-            for (int c = 0; c < NC; ++c) load_s(it + 2, c);
+        if (ib < nb && mbar_try_wait(empty_b(sb), phb ^ 1u)) {
+          const int per = BWD ? 3 * NC : NC;              // stages of ring B per tile: per chunk k, q, dO (or v)
+          const int it = ib / per, j = ib - it * per;
+          const int c = BWD ? j / 3 : j, which = BWD ? j - 3 * c : 0;
+          const CUtensorMap* tm = (BWD && which == 2) ? &tm_do : &tm_qkv;
+          const int col = BWD ? (which == 0 ? ck : cq) : cv;
+          mbar_arrive_expect_tx(full_b(sb), STAGE_B);
+          tma_load_3d_hint(sRingB + (uint32_t)sb * STAGE_B, tm, full_b(sb), col + 64 * c, 0, ((int)blockIdx.x + it * (int)gridDim.x), pol_once);
+          ++ib;
+          if (++sb == NSB) { sb = 0; phb ^= 1u; }
         }
-      } else {
-        for (int it = 0; it < n_my; ++it)
-          for (int c = 0; c < NC; ++c) {
-            if (BWD) {
-              load(&tm_qkv, ck + 64 * c, tile_of(it), pol_once);
-              load(&tm_qkv, cq + 64 * c, tile_of(it), pol_once);
-              load(&tm_do, cq + 64 * c, tile_of(it), pol_once);
-            } else {
-              load(&tm_qkv, cv + 64 * c, tile_of(it), pol_once);
-            }
-          }
       }
-      TPRINT("producer%d: total %lld cyc, waiting for a free stage %lld\n", (int)!ring_a, clock64() - t_begin, w_empty);
+      TPRINT("producer: total %lld cyc\n", clock64() - t_begin);
     }
-  } else if (warp == 9 || warp == 10) {
+  } else if (warp >= 9 && warp <= 11) {
     // ===================== MMA issuers =====================
     // Two issuing threads with their own operand ring each: warp 9 issues the score products (S, dP), warp 10 the chunk
     // products (P V, or dQ / dK / dV).  Every product is a handful of small MMAs behind two barrier waits and two
@@ -305,7 +290,7 @@ attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv,
       const uint32_t id_pk = idesc_bf16_m128(64u, false, true);
       const uint32_t id_ptk = idesc_bf16_m128(64u, true, true);
       int s = 0;
-      uint32_t ph = 0, nacc = 0;
+      uint32_t ph = 0;
       TDECL(w_full = 0, w_acc = 0, w_p = 0, t_begin = clock64());
       auto acquire = [&]() -> uint32_t {
         TWAIT(w_full, mbar_wait(do_a ? full_a(s) : full_b(s), ph, 2));
@@ -325,10 +310,12 @@ attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv,
         umma_commit(empty_a(s));
         advance();
       };
-      auto chunk_product = [&](uint32_t a_base, bool a_mn) {
-        const uint32_t b = acquire();
-        const uint32_t slot = nacc % NACC;
-        TWAIT(w_acc, mbar_wait(acc_empty(slot), ((nacc / NACC) & 1u) ^ 1u, 3));
+      auto chunk_product = [&](uint32_t n, uint32_t me, uint32_t a_base, bool a_mn) {
+        if ((n & 1u) != me) return;
+        const uint32_t sb = n % (uint32_t)NSB, slot = n % NACC;
+        TWAIT(w_full, mbar_wait(full_b(sb), (n / (uint32_t)NSB) & 1u, 2));
+        const uint32_t b = sRingB + sb * STAGE_B;
+        TWAIT(w_acc, mbar_wait(acc_empty(slot), ((n / NACC) & 1u) ^ 1u, 3));
         tcgen05_fence_after();
         const uint32_t d = tmem_base + acc_col(slot);
         const uint64_t db = desc_mnmajor(b, 8192u);
@@ -340,10 +327,8 @@ attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv,
             umma_bf16(d, desc_kmajor(a_base + (uint32_t)(j >> 2) * PANEL_B) + 2u * (j & 3), db + 128u * j, id_pk,
                       j > 0 ? 1u : 0u);
         }
-        umma_commit(empty_b(s));
-        advance();
+        umma_commit(empty_b(sb));
         umma_commit(acc_full(slot));
-        ++nacc;
       };
       if (do_a) {
         auto phase_s = [&](int it) {
@@ -367,23 +352,27 @@ attn_tc128_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv,
           if (it + 2 < n_my) phase_s(it + 2);
         }
       } else {
+        // chunk products n = 0, 1, 2, ... of this CTA in order; issuer j takes those with n % 2 == j.  Product n reads
+        // stage n % NSB of ring B (one stage per product) and writes accumulator slot n % NACC.
+        const uint32_t me = (uint32_t)(warp - 10);
+        uint32_t n = 0;
         for (int it = 0; it < n_my; ++it) {
           TWAIT(w_p, mbar_wait(p_full, (uint32_t)it & 1u, 4));  // P / dS of tile `it` written
           tcgen05_fence_after();
           for (int c = 0; c < NC; ++c) {
             if (BWD) {
-              chunk_product(sDS, false);  // dQ_c = dS K_c
-              chunk_product(sDS, true);   // dK_c = dS^T Q_c
-              chunk_product(sP, true);    // dV_c = P^T dO_c
+              chunk_product(n++, me, sDS, false);  // dQ_c = dS K_c
+              chunk_product(n++, me, sDS, true);   // dK_c = dS^T Q_c
+              chunk_product(n++, me, sP, true);    // dV_c = P^T dO_c
             } else {
-              chunk_product(sP, false);   // O_c = P V_c
+              chunk_product(n++, me, sP, false);   // O_c = P V_c
             }
           }
-          umma_commit(p_empty);  // P / dS may be overwritten once these products retire
+          umma_commit(p_empty);  // (one arrival per issuer) P / dS may be overwritten once these products retire
         }
       }
       TPRINT("mma%d    : total %lld cyc, waiting for operands %lld, for an accumulator slot %lld, for the softmax %lld (%d tiles)\n",
-             (int)!do_a, clock64() - t_begin, w_full, w_acc, w_p, n_my);
+             warp - 9, clock64() - t_begin, w_full, w_acc, w_p, n_my);
     }
   } else if (warp < 4) {
     // ===================== softmax warps: thread = score row =====================
@@ -666,13 +655,13 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
   static_assert(LP == 32 || LP == 64, "sub-tile kernel: 32 or 64 rows per window");
   constexpr int G = 128 / LP;
   constexpr int NC = DK / 64;
-  constexpr int NACC = BWD ? 3 : 4;
+  constexpr int NACC = BWD ? 2 : 4;  // even: slot n % NACC of product n is then private to issuer n % 2
   constexpr int MAXP = LP / 32;
   constexpr int NPROD = BWD ? 3 * NC : NC;
   constexpr uint32_t SUB_B = 8192;  // 64 rows x 128 B
   constexpr float LOG2E = 1.4426950408889634f;
   constexpr uint32_t DP_COL0 = 128u, DB_COL0 = 384u;
-  auto acc_col = [](uint32_t a) -> uint32_t { return BWD ? (a < 2 ? 256u + 64u * a : 448u) : 128u + 64u * a; };
+  auto acc_col = [](uint32_t a) -> uint32_t { return (BWD ? 256u : 128u) + 64u * a; };
 
   Params p = tp.p;
   p.offset += rng_step();
@@ -720,7 +709,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
     mbar_init(s_full(0), 1);
     mbar_init(s_full(1), 1);
     mbar_init(p_full, 4);
-    mbar_init(p_empty, 1);
+    mbar_init(p_empty, 2);  // one commit per chunk-product issuer
     for (int a = 0; a < NACC; ++a) {
       mbar_init(acc_full(a), 1);
       mbar_init(acc_empty(a), 4);
@@ -752,52 +741,47 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
   }
-  if (warp == 8 || warp == 11) {
-    // ===================== TMA producers: warp 8 feeds ring A, warp 11 ring B, each in its issuer's order =====================
+  if (warp == 8) {
+    // ===================== TMA producer: ONE thread feeds both rings, each in its consumers' order; it polls the two
+    // "stage free" barriers so that a full ring never holds up the other one =====================
     if (lane == 0) {
-      const bool ring_a = warp == 8;
-      const int n_s = ring_a ? NSA : NSB;
-      const uint32_t base = ring_a ? sRing : sRingB;
-      int s = 0;
-      uint32_t ph = 0;
-      auto load = [&](const CUtensorMap* tm, int col, int w0, uint64_t policy) {
-        const uint32_t fb = ring_a ? full_a(s) : full_b(s);
-        mbar_wait(ring_a ? empty_a(s) : empty_b(s), ph ^ 1u, 1);
-        mbar_arrive_expect_tx(fb, TILE_B);
-        tma_load_3d_hint(base + (uint32_t)s * TILE_B, tm, fb, col, 0, w0, policy);
-        if (++s == n_s) { s = 0; ph ^= 1u; }
-      };
+      const uint64_t pol_again = BWD ? L2_EVICT_LAST : L2_EVICT_FIRST, pol_once = L2_EVICT_FIRST;
       // backward: q, k, dO are read again by the chunk products of the same tile -> keep them in L2 until then;
       // everything that is read for the last time leaves L2 first
-      const uint64_t pol_again = BWD ? L2_EVICT_LAST : L2_EVICT_FIRST, pol_once = L2_EVICT_FIRST;
       const int cq = h * DK, ck = HD + h * DK, cv = 2 * HD + h * DK;
-      auto w0_of = [&](int it) { return ((int)blockIdx.x + it * (int)gridDim.x) * G; };
-      if (ring_a) {
-        auto load_a = [&](int it) {
-          for (int c = 0; c < NC; ++c) {
-            load(&tm_qkv, cq + 64 * c, w0_of(it), pol_again);
-            load(&tm_qkv, ck + 64 * c, w0_of(it), pol_again);
-            if (BWD) {
-              load(&tm_do, cq + 64 * c, w0_of(it), pol_again);
-              load(&tm_qkv, cv + 64 * c, w0_of(it), pol_once);
-            }
-          }
-        };
-        for (int it = 0; it < n_my; ++it) load_a(it);
-      } else {
-        for (int it = 0; it < n_my; ++it)
-          for (int c = 0; c < NC; ++c) {
-            if (BWD) {
-              load(&tm_qkv, ck + 64 * c, w0_of(it), pol_once);
-              load(&tm_qkv, cq + 64 * c, w0_of(it), pol_once);
-              load(&tm_do, cq + 64 * c, w0_of(it), pol_once);
-            } else {
-              load(&tm_qkv, cv + 64 * c, w0_of(it), pol_once);
-            }
-          }
+      const int na = n_my * (BWD ? 4 * NC : 2 * NC), nb = n_my * (BWD ? 3 * NC : NC);
+      int ia = 0, ib = 0, sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      TDECL(t_begin = clock64());
+      while (ia < na || ib < nb) {
+        if (ia < na && mbar_try_wait(empty_a(sa), pha ^ 1u)) {
+          const int per = BWD ? 4 * NC : 2 * NC;          // stages of ring A per tile: per chunk q, k [, dO, v]
+          const int it = ia / per, j = ia - it * per;
+          const int pc = BWD ? 4 : 2;
+          const int c = j / pc, which = j - c * pc;      // 0 q, 1 k, 2 dO, 3 v
+          const CUtensorMap* tm = which == 2 ? &tm_do : &tm_qkv;
+          const int col = which == 0 ? cq : which == 1 ? ck : which == 2 ? cq : cv;
+          const uint64_t pol = which == 3 ? pol_once : pol_again;
+          mbar_arrive_expect_tx(full_a(sa), TILE_B);
+          tma_load_3d_hint(sRing + (uint32_t)sa * TILE_B, tm, full_a(sa), col + 64 * c, 0, (((int)blockIdx.x + it * (int)gridDim.x) * G), pol);
+          ++ia;
+          if (++sa == NSA) { sa = 0; pha ^= 1u; }
+        }
+        if (ib < nb && mbar_try_wait(empty_b(sb), phb ^ 1u)) {
+          const int per = BWD ? 3 * NC : NC;              // stages of ring B per tile: per chunk k, q, dO (or v)
+          const int it = ib / per, j = ib - it * per;
+          const int c = BWD ? j / 3 : j, which = BWD ? j - 3 * c : 0;
+          const CUtensorMap* tm = (BWD && which == 2) ? &tm_do : &tm_qkv;
+          const int col = BWD ? (which == 0 ? ck : cq) : cv;
+          mbar_arrive_expect_tx(full_b(sb), TILE_B);
+          tma_load_3d_hint(sRingB + (uint32_t)sb * TILE_B, tm, full_b(sb), col + 64 * c, 0, (((int)blockIdx.x + it * (int)gridDim.x) * G), pol_once);
+          ++ib;
+          if (++sb == NSB) { sb = 0; phb ^= 1u; }
+        }
       }
+      TPRINT("producer: total %lld cyc\n", clock64() - t_begin);
     }
-  } else if (warp == 9 || warp == 10) {
+  } else if (warp >= 9 && warp <= 11) {
     // ===================== MMA issuers (see attn_tc128_kernel): warp 9 score products from ring A, warp 10 chunk
     // products from ring B =====================
     if (lane == 0) {
@@ -809,9 +793,10 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       const uint32_t id_pk = (idesc_bf16_m128(64u, false, true) & ~M128) | M64;
       const uint32_t id_ptk = (idesc_bf16_m128(64u, true, true) & ~M128) | M64;
       int s = 0;
-      uint32_t ph = 0, nacc = 0;
+      uint32_t ph = 0;
+      TDECL(w_full = 0, w_acc = 0, w_p = 0, t_begin = clock64());
       auto acquire = [&]() -> uint32_t {
-        mbar_wait(do_a ? full_a(s) : full_b(s), ph, 2);
+        TWAIT(w_full, mbar_wait(do_a ? full_a(s) : full_b(s), ph, 2));
         return base + (uint32_t)s * TILE_B;
       };
       auto advance = [&]() { if (++s == n_s) { s = 0; ph ^= 1u; } };
@@ -834,10 +819,12 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
         advance();
       };
       // per sub-tile g: slot_g (64 x 64) = A_g (P or dS, [64 x 64], K- or MN-major) * ring tile rows of g (MN-major B)
-      auto chunk_product = [&](uint32_t a_base, bool a_mn) {
-        const uint32_t b = acquire();
-        const uint32_t slot = nacc % NACC;
-        mbar_wait(acc_empty(slot), ((nacc / NACC) & 1u) ^ 1u, 3);
+      auto chunk_product = [&](uint32_t n, uint32_t me, uint32_t a_base, bool a_mn) {
+        if ((n & 1u) != me) return;
+        const uint32_t sb = n % (uint32_t)NSB, slot = n % NACC;
+        TWAIT(w_full, mbar_wait(full_b(sb), (n / (uint32_t)NSB) & 1u, 2));
+        const uint32_t b = sRingB + sb * TILE_B;
+        TWAIT(w_acc, mbar_wait(acc_empty(slot), ((n / NACC) & 1u) ^ 1u, 3));
         tcgen05_fence_after();
 #pragma unroll
         for (uint32_t g = 0; g < 2; ++g) {
@@ -848,10 +835,8 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
           for (int j = 0; j < 4; ++j)
             umma_bf16(d, da + (a_mn ? 128u : 2u) * j, db + 128u * j, a_mn ? id_ptk : id_pk, j > 0 ? 1u : 0u);
         }
-        umma_commit(empty_b(s));
-        advance();
+        umma_commit(empty_b(sb));
         umma_commit(acc_full(slot));
-        ++nacc;
       };
       if (do_a) {
         // score products of tile `it` into buffer it & 1, published to the softmax warps by the last chunk
@@ -865,26 +850,32 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
         };
         for (int it = 0; it < 2 && it < n_my; ++it) phase_a(it);
         for (int it = 0; it + 2 < n_my; ++it) {
-          mbar_wait(p_full, (uint32_t)it & 1u, 4);  // the softmax has finished reading S / dP buffer it & 1
+          TWAIT(w_p, mbar_wait(p_full, (uint32_t)it & 1u, 4));  // the softmax has finished reading S / dP buffer it & 1
           tcgen05_fence_after();
           phase_a(it + 2);
         }
       } else {
+        // chunk products n = 0, 1, 2, ... of this CTA in order; issuer j takes those with n % 2 == j.  Product n reads
+        // stage n % NSB of ring B (one stage per product) and writes accumulator slot n % NACC.
+        const uint32_t me = (uint32_t)(warp - 10);
+        uint32_t n = 0;
         for (int it = 0; it < n_my; ++it) {
-          mbar_wait(p_full, (uint32_t)it & 1u, 4);  // P / dS of tile `it` written
+          TWAIT(w_p, mbar_wait(p_full, (uint32_t)it & 1u, 4));  // P / dS of tile `it` written
           tcgen05_fence_after();
           for (int c = 0; c < NC; ++c) {
             if (BWD) {
-              chunk_product(sDS, false);  // dQ_c = dS K_c
-              chunk_product(sDS, true);   // dK_c = dS^T Q_c
-              chunk_product(sP, true);    // dV_c = P^T dO_c
+              chunk_product(n++, me, sDS, false);  // dQ_c = dS K_c
+              chunk_product(n++, me, sDS, true);   // dK_c = dS^T Q_c
+              chunk_product(n++, me, sP, true);    // dV_c = P^T dO_c
             } else {
-              chunk_product(sP, false);   // O_c = P V_c
+              chunk_product(n++, me, sP, false);   // O_c = P V_c
             }
           }
-          umma_commit(p_empty);  // P / dS may be overwritten once these products retire
+          umma_commit(p_empty);  // (one arrival per issuer) P / dS may be overwritten once these products retire
         }
       }
+      TPRINT("mma%d    : total %lld cyc, waiting for operands %lld, for an accumulator slot %lld, for the softmax %lld (%d tiles)\n",
+             warp - 9, clock64() - t_begin, w_full, w_acc, w_p, n_my);
     }
   } else if (warp < 4) {
     // ===================== softmax warps =====================
@@ -912,13 +903,14 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       for (int k = 0; k < MAXP; ++k) tmem_st_32x32b_x32(trow + DB_COL0 + 32u * k, z);
       tmem_st_wait();
     }
+    TDECL(w_s = 0, w_pe = 0, t_begin = clock64());
     for (int it = 0; it < n_my; ++it) {
       const int t = (int)blockIdx.x + it * (int)gridDim.x;
       const uint32_t b = (uint32_t)it & 1u;
       const int64_t w = (int64_t)t * G + wt;
       const bool valid = (i < L) && (w < p.W);
       const int64_t grow = (w * p.H + h) * (int64_t)L + i;
-      mbar_wait(s_full(b), ((uint32_t)it >> 1) & 1u, 5);
+      TWAIT(w_s, mbar_wait(s_full(b), ((uint32_t)it >> 1) & 1u, 5));
       tcgen05_fence_after();
       // ---- the whole score row in registers: e = exp2((s scale + bias) log2e - max) ; columns >= L come out as 0 ----
       float e[32 * MAXP];
@@ -1010,7 +1002,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
         }
         if (want_db) tmem_st_wait();
       }
-      if (it > 0) mbar_wait(p_empty, ((uint32_t)it - 1u) & 1u, 7);  // the products of the previous tile have read P (dS)
+      if (it > 0) TWAIT(w_pe, mbar_wait(p_empty, ((uint32_t)it - 1u) & 1u, 7));  // the products of the previous tile have read P (dS)
 #pragma unroll
       for (int c = 0; c < 4 * MAXP; ++c) {
         st_shared_v4(sPg + sw128(m, c0 + c), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
@@ -1023,6 +1015,8 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
+    if (threadIdx.x == 0)
+      TPRINT("softmax : total %lld cyc, waiting for S / dP %lld, for P / dS to be released %lld\n", clock64() - t_begin, w_s, w_pe);
     if (want_db) {
       const float unscale = 1.0f / p.scale;
 #pragma unroll
@@ -1048,12 +1042,13 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool leader = threadIdx.x == 4 * 32;
     uint32_t n = 0;
+    TDECL(w_af = 0, t_begin = clock64());
     for (int it = 0; it < n_my; ++it) {
       const int w0 = ((int)blockIdx.x + it * (int)gridDim.x) * G;
 #pragma unroll 1
       for (int prod = 0; prod < NPROD; ++prod, ++n) {
         const uint32_t slot = n % NACC;
-        mbar_wait(acc_full(slot), (n / NACC) & 1u, 6);
+        TWAIT(w_af, mbar_wait(acc_full(slot), (n / NACC) & 1u, 6));
         tcgen05_fence_after();
         uint32_t r0[32], r1[32];
         tmem_ld_32x32b_x32(trow + acc_col(slot), r0);
@@ -1094,6 +1089,7 @@ attn_tc64_kernel(const TcParams tp, const __grid_constant__ CUtensorMap tm_qkv, 
       }
     }
     if (leader) tma_wait_group<0>();
+    if (leader) TPRINT("epilogue: total %lld cyc, waiting for an accumulator %lld\n", clock64() - t_begin, w_af);
   }
 
   tcgen05_fence_before();
@@ -1159,16 +1155,19 @@ static int launch(const Params& p, cudaStream_t stream) {
     return LSTC_ERR_UNSUPPORTED;
   }
   // ring B (chunk-product operands): forward = v (first read, HBM-bound, a third of the loads); backward = k, q, dO
-  // re-read through L2 (short latency): three stages keep its issuer fed
-  int nsb = BWD ? 3 : (ns + 2) / 3;
+  // re-read through L2 (short latency).  Product n uses stage n % nsb and is issued by thread n % 2: nsb must be EVEN so
+  // that every stage (like every accumulator slot) is private to one issuing thread - a parity wait cannot tell two
+  // laps of a barrier apart, so consecutive uses of a stage have to be ordered by one thread's program order.
+  int nsb = BWD ? 4 : (((ns + 2) / 3 + 1) & ~1);
   {
     static const int nsb_env = [] {  // LSTC_ATTN_STAGES_B=<n>: depth of ring B (experiments)
       const char* e = getenv("LSTC_ATTN_STAGES_B");
       return e != nullptr ? atoi(e) : 0;
     }();
-    if (nsb_env > 0) nsb = nsb_env;
+    if (nsb_env > 0) nsb = nsb_env & ~1;
   }
   if (nsb < 2) nsb = 2;
+  if (ns - nsb < 3) nsb = 2;
   if (ns - nsb < 2) {
     set_last_error("attention: no shared memory left for the operand rings (L=%d)", p.L);
     return LSTC_ERR_UNSUPPORTED;

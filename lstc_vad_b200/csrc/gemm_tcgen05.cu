@@ -52,6 +52,9 @@ struct EpilogueParams {
   uint32_t drop_thr16;
   uint64_t seed, offset;
   int64_t drop_ld8;
+  uint64_t policy_a, policy_b;  // L2 eviction priority of the A / B operand loads
+  int n_major;                  // tile order: 0 = consecutive work items sweep N first (a wave holds few M panels and all
+                                // N panels: B is the operand re-read by every wave), 1 = sweep M first (A is re-read)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -104,6 +107,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies (createpolicy.fractional.L2::evict_* encodings for fraction 1.0, as in
+// cute::TMA::CacheHintSm90).  One operand of a GEMM is usually much smaller than the other and re-read by every wave of
+// tiles (the weight of a forward / dgrad product, the smaller activation of a wgrad product): it is loaded evict-last
+// so that it stays L2-resident across waves while the large operand streams through evict-first.
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int32_t c0,
+                                                 int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 // ---- cta_group::2 (CTA pair) variants ----
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -121,6 +139,14 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtenso
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(tmap), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2_hint(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int32_t c0,
+                                                     int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, "
+      "{%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(tmap), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
@@ -420,8 +446,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
         const int64_t tile = wi % (tiles_m * tiles_n);
         const int64_t split = wi / (tiles_m * tiles_n);
-        const int32_t m0 = (int32_t)((tile / tiles_n) * BLOCK_M);
-        const int32_t n0 = (int32_t)((tile % tiles_n) * BN);
+        const int32_t m0 = (int32_t)((ep.n_major ? tile % tiles_m : tile / tiles_n) * BLOCK_M);
+        const int32_t n0 = (int32_t)((ep.n_major ? tile / tiles_m : tile % tiles_n) * BN);
         const int64_t kb0 = split * kb_per_split;
         const int64_t kb1 = (kb0 + kb_per_split < num_kb_total) ? kb0 + kb_per_split : num_kb_total;
         for (int64_t kb = kb0; kb < kb1; ++kb) {
@@ -431,16 +457,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(smem_a(stage) + i * 8192, &tmap_a, full_bar(stage), m0 + i * 64, k0);
+              tma_load_2d_hint(smem_a(stage) + i * 8192, &tmap_a, full_bar(stage), m0 + i * 64, k0, ep.policy_a);
           } else {
-            tma_load_2d(smem_a(stage), &tmap_a, full_bar(stage), k0, m0);
+            tma_load_2d_hint(smem_a(stage), &tmap_a, full_bar(stage), k0, m0, ep.policy_a);
           }
           if (B_MN) {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(smem_b(stage) + i * 8192, &tmap_b, full_bar(stage), n0 + i * 64, k0);
+              tma_load_2d_hint(smem_b(stage) + i * 8192, &tmap_b, full_bar(stage), n0 + i * 64, k0, ep.policy_b);
           } else {
-            tma_load_2d(smem_b(stage), &tmap_b, full_bar(stage), k0, n0);
+            tma_load_2d_hint(smem_b(stage), &tmap_b, full_bar(stage), k0, n0, ep.policy_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -485,8 +511,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
       const int64_t tile = wi % (tiles_m * tiles_n);
       const int64_t split = wi / (tiles_m * tiles_n);
-      const int64_t m0 = (tile / tiles_n) * BLOCK_M;
-      const int64_t n0 = (tile % tiles_n) * BN;
+      const int64_t m0 = (ep.n_major ? tile % tiles_m : tile / tiles_n) * BLOCK_M;
+      const int64_t n0 = (ep.n_major ? tile / tiles_m : tile % tiles_n) * BN;
       const int64_t kb0 = split * kb_per_split;
       const bool has_k = kb0 < num_kb_total;  // an empty split contributes nothing
       const uint32_t acc = it & 1u;
@@ -599,8 +625,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters) {
         const int64_t tile = wi % (tiles_m * tiles_n);
         const int64_t split = wi / (tiles_m * tiles_n);
-        const int32_t m0 = (int32_t)((tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M);
-        const int32_t n0 = (int32_t)((tile % tiles_n) * BN + rank * HALF_N);
+        const int32_t m0 = (int32_t)((ep.n_major ? tile % tiles_m : tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M);
+        const int32_t n0 = (int32_t)((ep.n_major ? tile / tiles_m : tile % tiles_n) * BN + rank * HALF_N);
         const int64_t kb0 = split * kb_per_split;
         const int64_t kb1 = (kb0 + kb_per_split < num_kb_total) ? kb0 + kb_per_split : num_kb_total;
         for (int64_t kb = kb0; kb < kb1; ++kb) {
@@ -610,16 +636,16 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d_cg2(smem_a(stage) + i * 8192, &tmap_a, full_bar(stage), m0 + i * 64, k0);
+              tma_load_2d_cg2_hint(smem_a(stage) + i * 8192, &tmap_a, full_bar(stage), m0 + i * 64, k0, ep.policy_a);
           } else {
-            tma_load_2d_cg2(smem_a(stage), &tmap_a, full_bar(stage), k0, m0);
+            tma_load_2d_cg2_hint(smem_a(stage), &tmap_a, full_bar(stage), k0, m0, ep.policy_a);
           }
           if (B_MN) {
 #pragma unroll
             for (int i = 0; i < HALF_N / 64; ++i)
-              tma_load_2d_cg2(smem_b(stage) + i * 8192, &tmap_b, full_bar(stage), n0 + i * 64, k0);
+              tma_load_2d_cg2_hint(smem_b(stage) + i * 8192, &tmap_b, full_bar(stage), n0 + i * 64, k0, ep.policy_b);
           } else {
-            tma_load_2d_cg2(smem_b(stage), &tmap_b, full_bar(stage), k0, n0);
+            tma_load_2d_cg2_hint(smem_b(stage), &tmap_b, full_bar(stage), k0, n0, ep.policy_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -666,8 +692,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters, ++it) {
       const int64_t tile = wi % (tiles_m * tiles_n);
       const int64_t split = wi / (tiles_m * tiles_n);
-      const int64_t m0 = (tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M;
-      const int64_t n0 = (tile % tiles_n) * BN;
+      const int64_t m0 = (ep.n_major ? tile % tiles_m : tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M;
+      const int64_t n0 = (ep.n_major ? tile / tiles_m : tile % tiles_n) * BN;
       const int64_t kb0 = split * kb_per_split;
       const bool has_k = kb0 < num_kb_total;
       const uint32_t acc = it & 1u;
@@ -879,7 +905,32 @@ extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   ep.seed = seed;
   ep.offset = offset;
   ep.drop_ld8 = (N + 7) / 8;
-
+  {
+    // Tile order and L2 priorities.  The persistent CTAs work through the tiles in waves; with the N index running
+    // fastest a wave holds a few M panels (each read once overall) and ALL N panels, so the B operand is read again by
+    // every wave - and vice versa.  The operand that is re-read should be the SMALLER one, and it is loaded evict-last
+    // so that the re-reads come from L2 instead of DRAM while the larger operand streams through with normal priority
+    // (its lines are shared only by the tiles of one wave).  Measured before this (ncu, LTN step): the weight-gradient
+    // products read 1.6 - 2.3 x their operand bytes from DRAM (dW2 = gy^T h swept N first although h is the larger
+    // operand).  The evict-last hint is applied when the part of the small operand that one split touches fits
+    // comfortably in the 126 MB L2.  LSTC_GEMM_L2_HINTS=0 restores N-first order and plain loads (A/B measurements).
+    static const bool hints = [] {
+      const char* e = getenv("LSTC_GEMM_L2_HINTS");
+      return !(e != nullptr && e[0] == '0');
+    }();
+    ep.policy_a = ep.policy_b = gemm::L2_EVICT_NORMAL;
+    ep.n_major = 0;
+    const double bytes_a = 2.0 * (double)M * (double)K, bytes_b = 2.0 * (double)N * (double)K;
+    if (hints) {
+      const bool a_small = bytes_a < bytes_b;
+      ep.n_major = a_small ? 1 : 0;
+      const double small = a_small ? bytes_a : bytes_b;
+      if (small / (double)split_k < 72e6) {
+        if (a_small) ep.policy_a = gemm::L2_EVICT_LAST;
+        else ep.policy_b = gemm::L2_EVICT_LAST;
+      }
+    }
+  }
   const int64_t num_kb = (K + gemm::BLOCK_K - 1) / gemm::BLOCK_K;
   int splits = split_k;
   if (splits > num_kb) splits = (int)num_kb;
