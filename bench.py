@@ -289,12 +289,15 @@ def run_extras(args, wl, step, dev, world, rank, pg, B, steps, sync_all):
     return out
 
 
-def auc_delta_vs_oracle(wl, dev, train_steps: int = 8, test_windows: int = 640, lr_head: float = 2e-5,
-                        lr_encoder: float = 1e-6):
+def auc_delta_vs_oracle(wl, dev, train_steps: int = 12, test_windows: int = 384, lr_head: float = 3e-5,
+                        lr_encoder: float = 1.5e-6, checkpoints=(6, 9, 12)):
     """ROC-AUC delta at the headline width (BASELINE metric, second half): an LTN + Classifier at the workload's full
-    width is trained briefly on a synthetic split whose abnormal windows carry a feature bump, then a fixed test split
-    is scored by the CUDA path (eval mode) and by the CPU oracle with the same weights; AUCs by sklearn
-    (utils/eval_utils.py:21-24 uses roc_curve + auc).  Part of the cpu_baseline leg (the oracle is the checker)."""
+    width is trained briefly on a synthetic split whose abnormal windows carry a feature bump; at several checkpoints a
+    fixed test split is scored by the CUDA path (eval mode) and by the CPU oracle with the same weights; AUCs by sklearn
+    (utils/eval_utils.py:21-24 uses roc_curve + auc).  The delta is pure rank noise - bf16 moves every score by a few
+    1e-3, which swaps near-tied normal / abnormal pairs - so it depends on how well the scores are separated: it is
+    reported per checkpoint, and `value` is the one whose oracle AUC is closest to 0.97 (the reference's published
+    operating points are 0.98 / 0.86 / 0.76).  Part of the cpu_baseline leg (the oracle is the checker)."""
     import numpy as np
     import torch
     from sklearn.metrics import roc_auc_score
@@ -317,35 +320,40 @@ def auc_delta_vs_oracle(wl, dev, train_steps: int = 8, test_windows: int = 640, 
         x[is_anom] = xa
         return x, is_anom
 
+    xt, anom_t = batch(test_windows // 2, test_windows // 2, 0.5)   # the fixed test split
+    y = anom_t.numpy().astype(np.int32)
+    cfg = O.EncoderConfig(**{k: v for k, v in wl.encoder_kwargs().items() if k in O.EncoderConfig.__dataclass_fields__})
     # Adagrad's first steps move EVERY weight by ~lr in the gradient's direction: at the scripts' rates (1e-4 / 1e-2) the
     # softmax saturates on this synthetic split within a few steps (scores collapse to 0 / 1), so the brief training
-    # runs at smaller rates; what is checked is the DELTA between the two paths on non-degenerate, informative scores
+    # runs at smaller rates
     step = TrainStep(wl, dev, seed=3, train_mode=True, optimizer=True, lr_head=lr_head, lr_encoder=lr_encoder)
-    for _ in range(train_steps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    points = []
+    for i in range(1, train_steps + 1):
         x, anom = batch(Bt * P, Bt * P, 0.3)
         pseudo = anom[Bt * P:].float().view(Bt, P).repeat_interleave(T, dim=1)  # per-clip labels of the abnormal bags
         labs = losses.soft_clip_labels(pseudo, Bt, P, T)
+        step.encoder.train(); step.head.train()
         step.zero_grad()
         step.forward_backward(x.to(dev), labs.to(dev), Bt)
-    step.encoder.eval(); step.head.eval()
-    x, anom = batch(test_windows // 2, test_windows // 2, 0.5)
-    with torch.no_grad():
-        out = step.encoder(x.to(dev))
-        s_gpu = step.head(out[:, 0, :])[:, 1].float().cpu()
-        esd = {k: v.detach().cpu().float() if v.is_floating_point() else v.detach().cpu()
-               for k, v in step.encoder.state_dict().items()}
-        csd = {k: v.detach().cpu().float() for k, v in step.head.state_dict().items()}
-        cfg = O.EncoderConfig(**{k: v for k, v in wl.encoder_kwargs().items() if k in O.EncoderConfig.__dataclass_fields__})
-        torch.set_num_threads(os.cpu_count() or 1)
-        s_cpu = O.head_forward(csd, O.encoder_forward(esd, x, cfg)[:, 0, :], "classifier")[:, 1]
-    y = anom.numpy().astype(np.int32)
-    a_gpu, a_cpu = roc_auc_score(y, s_gpu.numpy()), roc_auc_score(y, s_cpu.numpy())
-    return {"value": abs(a_gpu - a_cpu), "auc_cuda": a_gpu, "auc_oracle_fp32": a_cpu, "bound": 1e-3,
-            "score_std": s_cpu.std().item(),
-            "score_max_abs_diff": (s_gpu - s_cpu).abs().max().item(), "windows": int(x.shape[0]),
-            "d_model": wl.d_model, "train_steps": train_steps,
-            "what": "window-level ROC-AUC of the CUDA path vs the fp32 CPU oracle with the same briefly trained weights on "
-                    "a fixed synthetic split (abnormal windows carry a feature bump)"}
+        if i in checkpoints:
+            step.encoder.eval(); step.head.eval()
+            with torch.no_grad():
+                s_gpu = step.head(step.encoder(xt.to(dev))[:, 0, :])[:, 1].float().cpu()
+                esd = {k: v.detach().cpu().float() if v.is_floating_point() else v.detach().cpu()
+                       for k, v in step.encoder.state_dict().items()}
+                csd = {k: v.detach().cpu().float() for k, v in step.head.state_dict().items()}
+                s_cpu = O.head_forward(csd, O.encoder_forward(esd, xt, cfg)[:, 0, :], "classifier")[:, 1]
+            a_gpu, a_cpu = roc_auc_score(y, s_gpu.numpy()), roc_auc_score(y, s_cpu.numpy())
+            points.append({"train_steps": i, "auc_cuda": a_gpu, "auc_oracle_fp32": a_cpu, "delta": abs(a_gpu - a_cpu),
+                           "score_std": s_cpu.std().item(), "score_max_abs_diff": (s_gpu - s_cpu).abs().max().item()})
+    best = min(points, key=lambda q: abs(q["auc_oracle_fp32"] - 0.97))
+    return {"value": best["delta"], "auc_cuda": best["auc_cuda"], "auc_oracle_fp32": best["auc_oracle_fp32"], "bound": 1e-3,
+            "score_std": best["score_std"], "score_max_abs_diff": best["score_max_abs_diff"], "windows": int(xt.shape[0]),
+            "d_model": wl.d_model, "train_steps": best["train_steps"], "checkpoints": points,
+            "what": "window-level ROC-AUC of the CUDA path vs the fp32 CPU oracle with the same briefly trained weights on a "
+                    "fixed synthetic split (abnormal windows carry a feature bump); `value` = the checkpoint whose oracle "
+                    "AUC is closest to 0.97, every checkpoint listed"}
 
 
 def main():
@@ -417,6 +425,11 @@ def main():
         step.forward_backward(f, l, B)
     sync_all()
 
+    # attention kernels alone, before the sustained passes push the board into its power cap (the same conditions as
+    # tools/kernel_bench.py): these kernels are partly issue-bound, so their time follows the SM clock
+    hbm_prof = hbm_kernels() if rank == 0 else {}
+    sync_all()
+
     # ---------------- device-resident timing (value) ----------------
     ops.LAUNCHES.reset()
     with ClockSampler(local_rank) as clocks:
@@ -448,6 +461,41 @@ def main():
     ms_prof = p0.elapsed_time(p1)
     gemm_prof = ops.PROFILE.collect()
     ops.PROFILE.disable()
+
+    # ---------------- the HBM-bound kernel family next to the GEMMs: fused attention, timed alone at the step's shape ------
+    def hbm_kernels():
+        """attention forward / backward of ONE layer at the workload's shape (train-mode dropout, rel-pos bias and its
+        gradient), CUDA events, L2 flushed between repetitions; algorithmic bytes = q,k,v read + o written (forward),
+        q,k,v,dO read + dq,dk,dv written (backward) - SURVEY.md section 8(d)."""
+        L_, H_, dk_ = wl.tokens_per_window + 1, wl.n_head, wl.d_k
+        rows = W * L_
+        qkv = torch.randn(rows, 3 * H_ * dk_, device=dev).to(torch.bfloat16)
+        do = torch.randn(rows, H_ * dk_, device=dev).to(torch.bfloat16)
+        bias = (torch.randn(H_, L_, L_, device=dev) * 0.1) if wl.relative_pe and wl.kind == "ltn" else None
+        pa = wl.dropouts[0] if not args.eval_mode else 0.0
+        drop = (pa, 1, 0) if pa > 0 else ops.NO_DROPOUT
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        scale_ = 1.0 / dk_ ** 0.5
+        unit = rows * H_ * dk_ * 2
+        out = {}
+        for name, fn, nbytes in (
+                ("attention_fwd", lambda: ops.attn_fwd(qkv, W, L_, H_, dk_, bias, scale_, drop), 4 * unit),
+                ("attention_bwd", lambda: ops.attn_bwd(qkv, do, W, L_, H_, dk_, bias, scale_, drop, bias is not None), 7 * unit)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(10):
+                flush.zero_()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                fn()
+                a1.record()
+                torch.cuda.synchronize()
+                tot += a0.elapsed_time(a1)
+            ms = tot / 10
+            out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6}
+        return out
 
     # ---------------- end-to-end: pinned host inputs, H2D each step (double-buffered), D2H of the loss -------------
     copy_stream = torch.cuda.Stream()
@@ -680,9 +728,12 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops_sustained"]) if achieved else None,
-                         # mean dram__bytes_read+write per GEMM launch over the 40 launches of one step (ncu capture in
-                         # profiles/r1_step_launches_traffic_v7_final.txt; algorithmic operand+result bytes average 0.80 GB)
-                         "traffic": 1.114e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
+                         # mean dram__bytes_read+write per GEMM launch over the 40 launches of one step: NOT measurable
+                         # in-run (needs ncu); taken from the committed capture of this same command,
+                         # profiles/r2_step_launches_traffic.txt (algorithmic operand+result bytes average 0.80 GB)
+                         "traffic": 0.983e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
+                         "traffic_source": "profiles/r2_step_launches_traffic.txt (ncu dram__bytes_read.sum + "
+                                           "dram__bytes_write.sum of `bench.py --steps 1 --warmup 3 --no-graph`)",
                          "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM launches of the pass)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained", "gemm_share_of_step": gms / ms_prof,
                          "measured": "CUDA-event pair around every GEMM launch during a second timed pass of the same K "
@@ -691,6 +742,10 @@ def main():
                          "by_operand_layout": by_kind, "model_tflops_whole_step": model_tflops},
             "clocks": (graph_clocks.summary() if (use_graph and graph_clocks is not None) else clocks.summary()),
         }
+        # second roofline: the HBM-bound fused attention kernels (tcgen05 / TMEM), timed alone, against the measured copy rate
+        line["roofline_hbm"] = {k: dict(v, peak_gbs=peaks["hbm_gbs"], frac=v["achieved_gbs"] / peaks["hbm_gbs"],
+                                        peak_source=peaks["source"] + " hbm_gbs")
+                                for k, v in hbm_prof.items()}
         line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             wps, cores, sample, _ = cpu_reference_windows_per_sec(wl, 32, 3, 1)
