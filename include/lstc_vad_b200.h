@@ -195,6 +195,11 @@ int lstc_weighted_auc(const float* scores, const float* pos_w, const float* neg_
  * ------------------------------------------------------------------------------------------- */
 int lstc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int lstc_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* dst[c, r] = bf16(src[r, c]) for an fp32 [rows, cols] matrix (pitches in elements): the transposed bf16 weight copy
+ * that the input-gradient products read as a K-major operand (dX = dY W of nn.Linear's backward; the reference runs it
+ * inside autograd for models/FFN.py:17-19, models/MultiHeadAttention.py:97-99,123). */
+int lstc_cast_f32_to_bf16_transposed(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                                     void* stream);
 /* out[c] = sum_r x[r, c] for bf16 x [rows, cols] (bias gradients); deterministic two-stage reduce.
  * workspace >= lstc_colsum_workspace(rows, cols) bytes. */
 int64_t lstc_colsum_workspace(int64_t rows, int64_t cols);

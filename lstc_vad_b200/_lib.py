@@ -46,6 +46,7 @@ SIGNATURES: dict[str, tuple] = {
     "lstc_weighted_auc": (_I, [_P, _P, _P, _L, _P, _P]),
     "lstc_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
     "lstc_cast_bf16_to_f32": (_I, [_P, _P, _L, _P]),
+    "lstc_cast_f32_to_bf16_transposed": (_I, [_P, _L, _P, _L, _L, _L, _P]),
     "lstc_colsum_workspace": (_L, [_L, _L]),
     "lstc_colsum_bf16": (_I, [_P, _L, _L, _L, _P, _P, _P]),
     "lstc_dropout_apply_bf16": (_I, [_P, _P, _L, _L, _F, _U, _U, _P]),

@@ -28,6 +28,26 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   for (int64_t i = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = __float2bfloat16(src[i]);
 }
+
+// dst[c, r] = bf16(src[r, c]) : transposed bf16 copy of an fp32 weight (the K-major B operand of the input-gradient
+// products).  64 x 64 tiles through shared memory: coalesced fp32 reads along c, coalesced bf16 writes along r.
+__global__ void cast_transpose_f32_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
+                                               int64_t ld_dst, int64_t rows, int64_t cols) {
+  __shared__ float tile[64][65];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    const int64_t r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    const int64_t c = c0 + ty + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[c * ld_dst + r] = __float2bfloat16(tile[tx][ty + i]);
+  }
+}
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
   const int64_t n8 = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -404,6 +424,19 @@ extern "C" int lstc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
   if (n == 0) return LSTC_OK;
   ew::cast_f32_bf16_kernel<<<ew::grid_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(
       src, (__nv_bfloat16*)dst, n);
+  LSTC_CHECK_LAUNCH();
+  return LSTC_OK;
+}
+extern "C" int lstc_cast_f32_to_bf16_transposed(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
+                                               int64_t cols, void* stream) {
+  LSTC_CHECK_ARG(rows == 0 || cols == 0 || (src && dst), "lstc_cast_f32_to_bf16_transposed: null pointer");
+  LSTC_CHECK_ARG(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= rows,
+                 "lstc_cast_f32_to_bf16_transposed: bad shape rows=%lld cols=%lld ld_src=%lld ld_dst=%lld", (long long)rows,
+                 (long long)cols, (long long)ld_src, (long long)ld_dst);
+  if (rows == 0 || cols == 0) return LSTC_OK;
+  LSTC_CHECK_ARG((cols + 63) / 64 < (1ll << 31) && (rows + 63) / 64 < 65536, "lstc_cast_f32_to_bf16_transposed: too large");
+  ew::cast_transpose_f32_bf16_kernel<<<dim3((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64)), 256, 0,
+                                       (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }

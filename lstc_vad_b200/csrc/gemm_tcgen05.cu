@@ -22,6 +22,7 @@
 // models/MultiHeadAttention.py:97-99,123-124, models/FFN.py:17-19 and models/Classifier.py:8.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/lstc_vad_b200.h"
@@ -34,7 +35,10 @@ constexpr int BLOCK_K = 64;          // one 128-byte swizzle atom of bf16 along 
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;     // 6 warps
 constexpr int NUM_EPI_WARPS = 4;
-constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+constexpr uint32_t SMEM_BUDGET = 192 * 1024;  // operand ring
+// epilogue staging for the TMA-store path: per epilogue warp two [32 rows x 64 cols] bf16 boxes (128-byte rows, SWIZZLE_128B)
+constexpr uint32_t EPI_BOX_BYTES = 32 * 128;
+constexpr uint32_t EPI_STAGE_BYTES = NUM_EPI_WARPS * 2 * EPI_BOX_BYTES;  // 32 KB
 
 struct EpilogueParams {
   void* C;                 // bf16 or fp32 [M, N]
@@ -53,6 +57,7 @@ struct EpilogueParams {
   uint64_t seed, offset;
   int64_t drop_ld8;
   uint64_t policy_a, policy_b;  // L2 eviction priority of the A / B operand loads
+  int tma_store;                // bf16 C leaves through shared memory + cp.async.bulk.tensor stores (tmap_c valid)
   int n_major;                  // tile order: 0 = consecutive work items sweep N first (a wave holds few M panels and all
                                 // N panels: B is the operand re-read by every wave), 1 = sweep M first (A is re-read)
 };
@@ -272,17 +277,60 @@ struct Config {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM cols");
 };
 
 // ------------------------------------------------------------------------------------------
-// Epilogue math on one 32-column chunk of one accumulator row
+// Epilogue.  One thread owns one accumulator row; a tile is drained in 32-column chunks:
+//   tcgen05.ld -> + bias -> ReLU -> * ReLU mask -> dropout -> + residual -> store
+// The mask / residual rows of chunk c+1 are requested before chunk c is processed (and those of a tile's first chunk
+// before the wait on its accumulator), so their DRAM latency is not on the drain path.  bf16 outputs are packed into a
+// per-warp [32 x 64] SWIZZLE_128B box in shared memory and leave with one cp.async.bulk.tensor store per 64 columns
+// (double-buffered; rows >= M and columns >= N are clipped by the tensor map); fp32 outputs (split-K partial sums, the
+// final fp32 activations) are written from registers.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, float (&v)[32], int64_t row,
-                                               int64_t col0, int64_t N) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void tma_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_PENDING) : "memory");
+}
+__device__ __forceinline__ void tma_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// mask / residual values of one 32-column chunk of one row (fast path: full chunk, 16-byte aligned rows)
+struct ChunkAux {
+  uint4 mask[4];
+  uint4 res[4];
+};
+
+__device__ __forceinline__ void aux_prefetch(const EpilogueParams& ep, int64_t row, int64_t col0, int64_t M, int64_t N,
+                                             ChunkAux& a) {
+  if (row >= M || col0 + 32 > N) return;
+  if (ep.relu_mask != nullptr && (ep.ld_mask % 8 == 0)) {
+    const uint4* mp = reinterpret_cast<const uint4*>(ep.relu_mask + row * ep.ld_mask + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.mask[j] = __ldg(mp + j);
+  }
+  if (ep.residual != nullptr && (ep.ld_res % 8 == 0)) {
+    const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + row * ep.ld_res + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.res[j] = __ldg(rp + j);
+  }
+}
+
+// everything between the accumulator and the store (row < M)
+__device__ __forceinline__ void epilogue_math(const EpilogueParams& ep, float (&v)[32], int64_t row, int64_t col0,
+                                              int64_t N, const ChunkAux& aux) {
   const bool full = (col0 + 32 <= N);
-  // + bias
   if (ep.bias != nullptr) {
     if (full) {
 #pragma unroll
@@ -301,17 +349,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, float (
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (ep.relu_mask != nullptr) {
-    const __nv_bfloat16* mrow = ep.relu_mask + row * ep.ld_mask + col0;
     if (full && (ep.ld_mask % 8 == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(mrow + j));
+      for (int j = 0; j < 4; ++j) {
         float f[8];
-        unpack8(m, f);
+        unpack8(aux.mask[j], f);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[j + t] = f[t] > 0.f ? v[j + t] : 0.f;
+        for (int t = 0; t < 8; ++t) v[8 * j + t] = f[t] > 0.f ? v[8 * j + t] : 0.f;
       }
     } else {
+      const __nv_bfloat16* mrow = ep.relu_mask + row * ep.ld_mask + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < N) v[j] = __bfloat162float(mrow[j]) > 0.f ? v[j] : 0.f;
@@ -327,23 +374,27 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, float (
     }
   }
   if (ep.residual != nullptr) {
-    const __nv_bfloat16* rrow = ep.residual + row * ep.ld_res + col0;
     if (full && (ep.ld_res % 8 == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(rrow + j));
+      for (int j = 0; j < 4; ++j) {
         float f[8];
-        unpack8(m, f);
+        unpack8(aux.res[j], f);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[j + t] += f[t];
+        for (int t = 0; t < 8; ++t) v[8 * j + t] += f[t];
       }
     } else {
+      const __nv_bfloat16* rrow = ep.residual + row * ep.ld_res + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < N) v[j] += __bfloat162float(rrow[j]);
     }
   }
-  // store
+}
+
+// store from registers (fp32 / split-K reduction / bf16 without a tensor map)
+__device__ __forceinline__ void epilogue_store_direct(const EpilogueParams& ep, const float (&v)[32], int64_t row,
+                                                      int64_t col0, int64_t N) {
+  const bool full = (col0 + 32 <= N);
   if (ep.c_is_f32) {
     float* crow = reinterpret_cast<float*>(ep.C) + row * ep.ldc + col0;
     if (ep.atomic_add) {
@@ -387,19 +438,88 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, float (
   }
 }
 
+// Drains one accumulator tile: rows [row0_warp, row0_warp + 32) of this warp (thread = row0_warp + lane), BN columns from
+// n0.  `tmem_tile` = TMEM address of this warp's lane quarter at the accumulator stage's first column; `stage_smem` = this
+// warp's two staging boxes; `n_stores` counts the warp's bulk stores (selects the staging box).
+template <int BN>
+__device__ __forceinline__ void drain_tile(const EpilogueParams& ep, const CUtensorMap* tmap_c, uint32_t tmem_tile,
+                                           uint32_t full_bar, uint32_t full_parity, int64_t row0_warp, int64_t n0,
+                                           int64_t M, int64_t N, bool has_k, uint32_t stage_smem, uint32_t& n_stores,
+                                           int lane) {
+  const int64_t row = row0_warp + lane;
+  const bool tma = ep.tma_store != 0;
+  ChunkAux cur, nxt;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cur.mask[j] = cur.res[j] = nxt.mask[j] = nxt.res[j] = make_uint4(0u, 0u, 0u, 0u);
+  aux_prefetch(ep, row, n0, M, N, cur);
+  mbar_wait(full_bar, full_parity);
+  tcgen05_fence_after();
+  uint32_t box = stage_smem + (n_stores & 1u) * EPI_BOX_BYTES;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int64_t col0 = n0 + c * 32;
+    if (col0 >= N) break;  // warp-uniform
+    if (c + 1 < BN / 32) aux_prefetch(ep, row, col0 + 32, M, N, nxt);
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_tile + c * 32, r);
+    tmem_ld_wait();
+    if (tma && (c & 1) == 0) {
+      // the box used two stores ago must have been read out of shared memory
+      box = stage_smem + (n_stores & 1u) * EPI_BOX_BYTES;
+      if (lane == 0) tma_wait_group_read<1>();
+      __syncwarp();
+    }
+    if (row < M) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
+      epilogue_math(ep, v, row, col0, N, cur);
+      if (tma) {
+        // 16-byte unit u of the 128-byte row goes to unit u ^ (row & 7) (SWIZZLE_128B; the box is 1024-byte aligned)
+        const uint32_t rbase = box + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f[t] = v[8 * j + t];
+          const uint32_t u = (uint32_t)((c & 1) * 4 + j) ^ ((uint32_t)lane & 7u);
+          st_shared_v4(rbase + u * 16u, pack8(f));
+        }
+      } else {
+        epilogue_store_direct(ep, v, row, col0, N);
+      }
+    }
+    if (tma && ((c & 1) == 1 || col0 + 32 >= N)) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row0_warp < M) {
+        tma_store_2d(tmap_c, box, (int32_t)(col0 - (c & 1) * 32), (int32_t)row0_warp);
+        tma_commit_group();
+      }
+      ++n_stores;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cur.mask[j] = nxt.mask[j];
+      cur.res[j] = nxt.res[j];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
+                         const __grid_constant__ CUtensorMap tmap_c, int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
   using Cfg = Config<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_smem = smem_base + STAGES * Cfg::STAGE_BYTES;  // TMA-store staging boxes
+  const uint32_t bar_base = epi_smem + EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -421,6 +541,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -507,6 +628,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue warps =====================
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const uint32_t stage_smem = epi_smem + (uint32_t)q * 2u * EPI_BOX_BYTES;
+    uint32_t n_stores = 0;
     uint32_t it = 0;
     for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
       const int64_t tile = wi % (tiles_m * tiles_n);
@@ -517,27 +640,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool has_k = kb0 < num_kb_total;  // an empty split contributes nothing
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      const int64_t row = m0 + q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int64_t col0 = n0 + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        if (row < M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
-          epilogue_chunk(ep, v, row, col0, N);
-        }
-      }
+      drain_tile<BN>(ep, &tmap_c, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, tmem_full_bar(acc), acc_phase,
+                     m0 + q * 32, n0, M, N, has_k, stage_smem, n_stores, lane);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
     }
+    if (lane == 0) tma_wait_group_all();  // bulk stores still reading shared memory / in flight
   }
 
   // teardown
@@ -561,19 +670,20 @@ struct Config2 {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                              int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
+                              const __grid_constant__ CUtensorMap tmap_c, int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
   using Cfg = Config2<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF_N = BN / 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_smem = smem_base + STAGES * Cfg::STAGE_BYTES;  // TMA-store staging boxes
+  const uint32_t bar_base = epi_smem + EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -599,6 +709,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (ep.tma_store) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);   // leader's copy is the one in use: its producer's arrive.expect_tx
       mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit from the leader
@@ -688,6 +799,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   } else {
     // ===================== epilogue warps (both CTAs; each drains its own 128 TMEM lanes) =====================
     const int q = warp_idx & 3;
+    const uint32_t stage_smem = epi_smem + (uint32_t)q * 2u * EPI_BOX_BYTES;
+    uint32_t n_stores = 0;
     uint32_t it = 0;
     for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters, ++it) {
       const int64_t tile = wi % (tiles_m * tiles_n);
@@ -698,27 +811,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       const bool has_k = kb0 < num_kb_total;
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      const int64_t row = m0 + q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int64_t col0 = n0 + c * 32;
-        if (col0 >= N) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        if (row < M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
-          epilogue_chunk(ep, v, row, col0, N);
-        }
-      }
+      drain_tile<BN>(ep, &tmap_c, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, tmem_full_bar(acc), acc_phase,
+                     m0 + q * 32, n0, M, N, has_k, stage_smem, n_stores, lane);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
     }
+    if (lane == 0) tma_wait_group_all();
   }
 
   // teardown: nobody may free TMEM / exit while the peer can still signal or read
@@ -732,53 +831,40 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
-  }
-  return fn;
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
+// box = [box_rows, 64 cols], SWIZZLE_128B, zero fill out of bounds.  Encoded maps are cached per
+// (pointer, shape, pitch, box) in runtime.cu (thread-safe), so a training job's repeating launches skip the driver call.
+static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows) {
+  const uint64_t gdim[2] = {(uint64_t)cols, (uint64_t)rows};
+  const uint64_t gstride[1] = {(uint64_t)ld * 2};
+  const uint32_t box[2] = {64u, box_rows};
+  return encode_tmap_bf16_sw128(tm, ptr, 2, gdim, gstride, box, 256);
 }
 
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
-// box = [box_rows, 64 cols], SWIZZLE_128B, zero fill out of bounds.
-static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) {
-    set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver");
-    return LSTC_ERR_DRIVER;
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, box_rows};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%u",
-                   (int)r, ptr, (long long)rows, (long long)cols, (long long)ld, box_rows);
-    return LSTC_ERR_DRIVER;
-  }
-  return LSTC_OK;
+// bf16 outputs with a TMA-compatible pitch leave through shared memory + bulk tensor stores: map over C [M, N] with
+// [32 rows x 64 cols] SWIZZLE_128B boxes.  LSTC_GEMM_TMA_STORE=0 keeps the register stores (A/B measurements).
+static int make_tmap_c(CUtensorMap* tc, EpilogueParams& ep, int64_t M, int64_t N) {
+  const char* e = getenv("LSTC_GEMM_TMA_STORE");  // read per call: A/B measurements flip it inside one process
+  const bool enabled = !(e != nullptr && e[0] == '0');
+  memset(tc, 0, sizeof(*tc));
+  ep.tma_store = 0;
+  if (!enabled || ep.c_is_f32 || ep.ldc % 8 != 0 || N < 64 || M < 32) return LSTC_OK;
+  const uint64_t gdim[2] = {(uint64_t)N, (uint64_t)M};
+  const uint64_t gstride[1] = {(uint64_t)ep.ldc * 2};
+  const uint32_t box[2] = {64u, 32u};
+  const int rc = encode_tmap_bf16_sw128(tc, ep.C, 2, gdim, gstride, box, 256);
+  if (rc == LSTC_OK) ep.tma_store = 1;
+  return rc;
 }
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                  int splits, const EpilogueParams& ep, cudaStream_t stream) {
+                  int splits, const EpilogueParams& ep_in, cudaStream_t stream) {
   using Cfg = Config<BN>;
-  CUtensorMap ta, tb;
-  int rc;
+  CUtensorMap ta, tb, tc;
+  EpilogueParams ep = ep_in;
+  int rc = make_tmap_c(&tc, ep, M, N);
+  if (rc != LSTC_OK) return rc;
   // K-major operand: matrix is [MN, K]; MN-major operand: matrix is [K, MN]
   rc = A_MN ? make_tmap(&ta, A, K, M, lda, BLOCK_K) : make_tmap(&ta, A, M, K, lda, BLOCK_M);
   if (rc != LSTC_OK) return rc;
@@ -795,7 +881,7 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_
   const int64_t tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * splits;
   int grid = num_sms();
   if (tiles < grid) grid = (int)tiles;
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, splits, ep);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, M, N, K, splits, ep);
   LSTC_CHECK_LAUNCH();
   return LSTC_OK;
 }
@@ -811,10 +897,12 @@ static bool use_2cta() {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch2(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                   int splits, const EpilogueParams& ep, cudaStream_t stream) {
+                   int splits, const EpilogueParams& ep_in, cudaStream_t stream) {
   using Cfg = Config2<BN>;
-  CUtensorMap ta, tb;
-  int rc;
+  CUtensorMap ta, tb, tc;
+  EpilogueParams ep = ep_in;
+  int rc = make_tmap_c(&tc, ep, M, N);
+  if (rc != LSTC_OK) return rc;
   rc = A_MN ? make_tmap(&ta, A, K, M, lda, BLOCK_K) : make_tmap(&ta, A, M, K, lda, BLOCK_M);
   if (rc != LSTC_OK) return rc;
   rc = B_MN ? make_tmap(&tb, B, K, N, ldb, BLOCK_K) : make_tmap(&tb, B, N, K, ldb, BN / 2);
@@ -842,7 +930,7 @@ static int launch2(const void* A, int64_t lda, const void* B, int64_t ldb, int64
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LSTC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, splits, ep));
+  LSTC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, splits, ep));
   return LSTC_OK;
 }
 

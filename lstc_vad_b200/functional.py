@@ -14,6 +14,8 @@ parameter version), GEMMs accumulate in fp32, LayerNorm / softmax / losses compu
 """
 from __future__ import annotations
 
+import os
+
 import threading
 import weakref
 from dataclasses import dataclass
@@ -140,6 +142,21 @@ class WeightCache:
             return buf
         return self._get(("qkv", id(wq), id(wk), id(wv), wq.device.index), (wq, wk, wv), build)
 
+    def bf16_t(self, p: torch.Tensor) -> torch.Tensor:
+        """p fp32 [R,C] -> bf16 [C,R]: the transposed copy the input-gradient product dX = dY W reads as a K-major
+        operand (opt-in, see DGRAD_TRANSPOSED_W)."""
+        return self._get(("bf16_t", id(p), p.device.index), (p,), lambda: ops.cast_to_bf16_transposed(p.detach()))
+
+    def qkv_t(self, wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor) -> torch.Tensor:
+        """[w_qs; w_ks; w_vs]^T as one bf16 [D, 3*H*dk] matrix (dX of the fused QKV projection)."""
+        def build():
+            n = wq.shape[0]
+            buf = torch.empty((wq.shape[1], 3 * n), device=wq.device, dtype=BF16)
+            for i, w in enumerate((wq, wk, wv)):
+                ops.cast_to_bf16_transposed(w.detach(), out=buf[:, i * n:(i + 1) * n])
+            return buf
+        return self._get(("qkv_t", id(wq), id(wk), id(wv), wq.device.index), (wq, wk, wv), build)
+
     def f32_padded(self, p: torch.Tensor, pad: int) -> torch.Tensor:
         def build():
             if pad == 0:
@@ -179,6 +196,20 @@ def _wgrad_split(n_out: int, k_out: int, m_red: int, n_units: int = 74) -> int:
         if eff > best_eff + 1e-9:
             best, best_eff = s, eff
     return best
+
+
+# dX = dY W reads the row-major bf16 weight as an MN-major B operand.  DGRAD_TRANSPOSED_W = True (or the environment
+# variable LSTC_DGRAD_TRANSPOSED_W=1) switches to a cached transposed copy (K-major B, the forward products' layout):
+# alone, those products run 1 - 5 % faster (tools/gemm_ab.py), but the whole train step does not (power-capped, and the
+# extra transposed casts of every weight version cost what the products gain), so it is opt-in.
+DGRAD_TRANSPOSED_W = os.environ.get("LSTC_DGRAD_TRANSPOSED_W", "0") == "1"
+
+
+def _dgrad(dy: torch.Tensor, w: torch.Tensor, **epilogue) -> torch.Tensor:
+    """dX[m,k] = sum_n dy[m,n] w[n,k] for an nn.Linear weight w [n,k] (fp32 parameter), fused epilogue passed through."""
+    if DGRAD_TRANSPOSED_W:
+        return ops.gemm(dy, CACHE.bf16_t(w), **epilogue)
+    return ops.gemm(dy, CACHE.bf16(w), b_mn=True, **epilogue)
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -318,14 +349,17 @@ class MHABlockFn(torch.autograd.Function):
             gy1d = ops.dropout_apply(g2, cfg.fc_drop) if cfg.fc_drop[0] > 0 else None
         gfc = gy1d if gy1d is not None else gy1
         dwfc = _wgrad(gfc, o)                                   # [D, HD]
-        do = ops.gemm(gfc, CACHE.bf16(wfc), b_mn=True)          # [M, HD]
+        do = _dgrad(gfc, wfc)                                   # [M, HD]
         bias = ops.relbias_gather(table.detach(), index, L) if ctx.has_bias else None
         need_dtable = ctx.has_bias and ctx.needs_input_grad[7]
         dqkv, dbias = ops.attn_bwd(qkv, do, W, L, H, dk, bias, ctx.scale, cfg.attn_drop, need_dtable)
         dwqkv = _wgrad(dqkv, x2)                                # [3HD, D]
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = ops.gemm(dqkv, CACHE.qkv(wq, wk, wv), b_mn=True, residual=gy1).view(W, L, D)
+            if DGRAD_TRANSPOSED_W:
+                gx = ops.gemm(dqkv, CACHE.qkv_t(wq, wk, wv), residual=gy1).view(W, L, D)
+            else:
+                gx = ops.gemm(dqkv, CACHE.qkv(wq, wk, wv), b_mn=True, residual=gy1).view(W, L, D)
         dtable = ops.relbias_scatter(dbias, index, table.shape[0]) if need_dtable else None
         return (gx, dwqkv[:HD], dwqkv[HD:2 * HD], dwqkv[2 * HD:], dwfc, dlnw, dlnb, dtable, None, None)
 
@@ -444,12 +478,18 @@ class FFNBlockFn(torch.autograd.Function):
             gin = gy2d if gy2d is not None else gy2
             db2 = ops.colsum(gin)
         dw2 = _wgrad(gin, h)                                                  # [D, Dh+pad]
-        dh = ops.gemm(gin, CACHE.bf16(w2, pad_cols=pad), b_mn=True, relu_mask=h)   # [M, Dh+pad]
+        if pad == 0:
+            dh = _dgrad(gin, w2, relu_mask=h)                                 # [M, Dh]
+        else:
+            dh = ops.gemm(gin, CACHE.bf16(w2, pad_cols=pad), b_mn=True, relu_mask=h)   # [M, Dh+pad]
         db1 = ops.colsum(dh)
         dw1 = _wgrad(dh, x2)                                                  # [Dh+pad, D]
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = ops.gemm(dh, CACHE.bf16(w1, pad_rows=pad), b_mn=True, residual=gy2).view(ctx.shape)
+            if pad == 0:
+                gx = _dgrad(dh, w1, residual=gy2).view(ctx.shape)
+            else:
+                gx = ops.gemm(dh, CACHE.bf16(w1, pad_rows=pad), b_mn=True, residual=gy2).view(ctx.shape)
         if pad:
             dw2, dw1, db1 = dw2[:, :Dh].contiguous(), dw1[:Dh], db1[:Dh]
         return gx, dw1, db1, dw2, db2, dlnw, dlnb, None

@@ -497,6 +497,24 @@ def cast_to_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+def cast_to_bf16_transposed(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [R, C] -> bf16 [C, R] (out may be a row-major view with a wider pitch)."""
+    lib = _lib.load()
+    _cuda(x, "x", F32)
+    ld_src = _rowmajor2d(x, "x")
+    R, C = x.shape
+    if out is None:
+        out = torch.empty((C, R), device=x.device, dtype=BF16)
+    else:
+        _cuda(out, "out", BF16)
+        if tuple(out.shape) != (C, R):
+            raise RuntimeError(f"lstc_vad_b200.cast_to_bf16_transposed: out has shape {tuple(out.shape)}, expected {(C, R)}")
+    st = lib.lstc_cast_f32_to_bf16_transposed(_p(x), ld_src, _p(out), _rowmajor2d(out, "out"), R, C, _stream())
+    _lib.check(st, "lstc_cast_f32_to_bf16_transposed")
+    LAUNCHES.add(1)
+    return out
+
+
 def cast_to_f32(x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _cuda(x, "x", BF16)

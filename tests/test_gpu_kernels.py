@@ -66,6 +66,25 @@ def test_gemm_bf16_out(ops):
     assert_close("gemm bf16 out", got, a.float() @ b.float().t(), rtol=1e-2, atol=0.3)
 
 
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES + [(31, 64, 64), (33, 72, 64), (257, 328, 192), (5000, 4096, 128)])
+def test_gemm_bf16_out_all_shapes(ops, M, N, K):
+    """bf16 outputs leave through shared memory + TMA bulk stores when the pitch allows (ragged M / N are clipped by the
+    tensor map); narrow or unaligned outputs take the register-store path.  Same numbers either way."""
+    a, b = _rand((M, K), 1.0, 31), _rand((N, K), 0.1, 32)
+    bias = _rand((N,), 1.0, 33, F32)
+    res = _rand((M, N), 1.0, 34)
+    mask = torch.relu(_rand((M, N), 1.0, 35))
+    ref = ((a.float() @ b.float().t() + bias) * (mask.float() > 0) + res.float()).to(BF16)
+    got = ops.gemm(a, b, bias=bias, relu_mask=mask, residual=res)
+    assert got.dtype == BF16
+    assert_close(f"gemm bf16 out {M}x{N}x{K}", got, ref.float(), rtol=1e-2, atol=3e-2)
+    # into a column slice of a wider buffer (pitch > N): the neighbouring columns stay untouched
+    wide = torch.full((M, N + 16), 7.0, device="cuda", dtype=BF16)
+    ops.gemm(a, b, bias=bias, relu_mask=mask, residual=res, out=wide[:, 8:8 + N])
+    assert torch.equal(wide[:, 8:8 + N], got)
+    assert (wide[:, :8] == 7).all() and (wide[:, 8 + N:] == 7).all()
+
+
 def test_gemm_epilogue_bias_relu_residual(ops):
     M, N, K = 777, 1032, 520
     a, b = _rand((M, K), 1.0, 5), _rand((N, K), 0.05, 6)
@@ -336,6 +355,17 @@ def test_cls_prepend(ops, W, L0, D, dt):
     assert_close("cls prepend bwd dx (learned)", dx2, g.float()[:, 1:], rtol=1e-5, atol=1e-5)
     assert_close("cls prepend bwd dcls", dcls2, g.float()[:, 0].sum(0), rtol=1e-4, atol=1e-3)
     assert_close("cls prepend bwd dpos", dpos2, g.float().sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("R,C", [(64, 64), (2048, 4096), (100, 37), (3027, 520), (1, 9)])
+def test_cast_transposed_is_bit_exact(ops, R, C):
+    x = _rand((R, C), 1.0, 41, F32)
+    assert torch.equal(ops.cast_to_bf16_transposed(x), x.to(BF16).t().contiguous())
+    # source = row slice of a taller matrix, destination = column slice of a wider one (the fused [D, 3*H*dk] QKV^T buffer)
+    wide = torch.full((C, 3 * R + 8), 3.0, device="cuda", dtype=BF16)
+    ops.cast_to_bf16_transposed(x, out=wide[:, R:2 * R])
+    assert torch.equal(wide[:, R:2 * R], x.to(BF16).t())
+    assert (wide[:, :R] == 3).all() and (wide[:, 2 * R:] == 3).all()
 
 
 def test_casts_colsum_scale(ops):

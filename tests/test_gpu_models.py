@@ -459,3 +459,30 @@ def test_mil_loss_flat_column_form_of_spatio_MIL_CE(L):
     plain = ~part_of_max
     assert torch.all(y.grad[:B, 0][plain[:B]] == 0)
     assert torch.allclose(y.grad[B:, 0][plain[B:]], torch.full_like(y.grad[B:, 0][plain[B:]], 0.01 / (n - B)), rtol=1e-5)
+
+
+def test_dgrad_against_transposed_weight_copies_gives_the_same_gradients(M):
+    """Opt-in functional.DGRAD_TRANSPOSED_W: dX = dY W against cached transposed bf16 weight copies (K-major operand)
+    instead of the row-major weight read MN-major.  Same products in the same k order: equal gradients."""
+    from lstc_vad_b200 import functional as Fn
+    kw = dict(n_layers=2, n_head=4, d_k=64, d_v=64, d_model=256, d_inner=512, MHA_attn_dropout=0.0, MHA_fc_dropout=0.0,
+              FFN_dropout=0.0, position_dropout=0.0, relative_pe=True, window_size=2, window_depth=3)
+    torch.manual_seed(5)
+    enc = M.Encoder(**kw).cuda().eval()
+    x = torch.randn(24, 12, 256, generator=torch.Generator().manual_seed(6)).cuda()
+    grads = []
+    try:
+        for flag in (False, True):
+            Fn.DGRAD_TRANSPOSED_W = flag
+            Fn.invalidate_weight_cache()
+            enc.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            enc(xi)[:, 0, :].float().square().sum().backward()
+            grads.append([xi.grad.clone()] + [p.grad.clone() for p in enc.parameters() if p.grad is not None])
+    finally:
+        Fn.DGRAD_TRANSPOSED_W = False
+        Fn.invalidate_weight_cache()
+    assert len(grads[0]) == len(grads[1]) > 10
+    for a, b in zip(*grads):
+        err = ((a.double() - b.double()).norm() / a.double().norm().clamp_min(1e-30)).item()
+        assert err < 1e-3, err
