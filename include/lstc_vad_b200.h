@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTC_ABI_VERSION 1
+#define LSTC_ABI_VERSION 2
 
 int lstc_abi_version(void);
 const char* lstc_last_error(void);
@@ -47,12 +47,19 @@ int lstc_set_rng_step(const void* counter_dev);
  *   epilogue order: + bias[N] -> relu -> (relu_mask > 0 ? v : 0) -> dropout(p) -> + residual -> store
  *   c_is_f32 = 0 : C bf16, 1 : C fp32.   split_k > 1 (fp32 C only, no epilogue): C is zero-filled and
  *   partial sums are combined with red.add;  accumulate = 1 adds into the existing C.
+ *   colsum (fp32 [N], 8-byte aligned, or NULL): colsum[n] += sum_m C[m,n] of the stored bf16 values, accumulated in the
+ *   epilogue (the bias gradient of the Linear whose input gradient this product is, models/FFN.py:17 w_1); only where
+ *   lstc_gemm_bf16_fuses_colsum() returns 1, and the caller zero-fills it.
  * Requirements: lda, ldb multiples of 8; A, B, C 16-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int64_t M, int64_t N, int64_t K, void* C, int64_t ldc, int c_is_f32, const float* bias,
                    int relu, const void* relu_mask, int64_t ld_mask, const void* residual, int64_t ld_res,
-                   float dropout_p, uint64_t seed, uint64_t offset, int split_k, int accumulate, void* stream);
+                   float dropout_p, uint64_t seed, uint64_t offset, int split_k, int accumulate, float* colsum,
+                   void* stream);
+/* 1 when the product above can fuse the column sums for this output (bf16 C, ldc % 8 == 0, M >= 32, N >= 64: the
+ * shared-memory + TMA-store epilogue), else 0 (run lstc_colsum on C instead). */
+int lstc_gemm_bf16_fuses_colsum(int64_t M, int64_t N, int64_t ldc, int c_is_f32);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused short-sequence attention, one CTA per (window-group, head).

@@ -24,7 +24,8 @@ SIGNATURES: dict[str, tuple] = {
     "lstc_last_error": (c_char_p, []),
     "lstc_set_rng_step": (_I, [_P]),
     "lstc_gemm_bf16": (_I, [_P, _L, _I, _P, _L, _I, _L, _L, _L, _P, _L, _I, _P, _I, _P, _L, _P, _L, _F, _U, _U,
-                            _I, _I, _P]),
+                            _I, _I, _P, _P]),
+    "lstc_gemm_bf16_fuses_colsum": (_I, [_L, _L, _L, _I]),
     "lstc_attn_fwd": (_I, [_P, _L, _L, _I, _I, _I, _P, _F, _F, _U, _U, _P, _L, _P, _P]),
     "lstc_attn_bwd": (_I, [_P, _L, _P, _L, _L, _I, _I, _I, _P, _F, _F, _U, _U, _P, _L, _P, _P]),
     "lstc_attn_cls_fwd": (_I, [_P, _L, _P, _P, _L, _L, _I, _I, _I, _F, _F, _U, _U, _P, _L, _P]),
@@ -86,7 +87,7 @@ def load() -> ctypes.CDLL:
                 fn = getattr(lib, name)  # raises AttributeError if the symbol is not exported
                 fn.restype = res
                 fn.argtypes = args
-            if lib.lstc_abi_version() != 1:
+            if lib.lstc_abi_version() != 2:
                 raise ImportError("liblstc_vad_b200.so ABI version mismatch; rebuild")
             _lib = lib
     return _lib

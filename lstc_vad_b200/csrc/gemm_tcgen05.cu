@@ -57,6 +57,7 @@ struct EpilogueParams {
   uint64_t seed, offset;
   int64_t drop_ld8;
   uint64_t policy_a, policy_b;  // L2 eviction priority of the A / B operand loads
+  float* colsum;                // [N] fp32 or null: += column sums of the stored bf16 C (TMA-store path only)
   int tma_store;                // bf16 C leaves through shared memory + cp.async.bulk.tensor stores (tmap_c valid)
   int n_major;                  // tile order: 0 = consecutive work items sweep N first (a wave holds few M panels and all
                                 // N panels: B is the operand re-read by every wave), 1 = sweep M first (A is re-read)
@@ -488,13 +489,39 @@ __device__ __forceinline__ void drain_tile(const EpilogueParams& ep, const CUten
       } else {
         epilogue_store_direct(ep, v, row, col0, N);
       }
+    } else if (tma && ep.colsum != nullptr) {
+      // rows past M are clipped by the store but would enter the column sums: stage zeros
+      const uint32_t rbase = box + (uint32_t)lane * 128u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(rbase + ((uint32_t)((c & 1) * 4 + j) ^ ((uint32_t)lane & 7u)) * 16u, make_uint4(0u, 0u, 0u, 0u));
     }
     if (tma && ((c & 1) == 1 || col0 + 32 >= N)) {
+      const int64_t gcol0 = col0 - (c & 1) * 32;  // first column of the 64-column box
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && row0_warp < M) {
-        tma_store_2d(tmap_c, box, (int32_t)(col0 - (c & 1) * 32), (int32_t)row0_warp);
+        tma_store_2d(tmap_c, box, (int32_t)gcol0, (int32_t)row0_warp);
         tma_commit_group();
+      }
+      if (ep.colsum != nullptr) {
+        // column sums of the staged bf16 box (what the consumer of C will read): lane l owns columns 2l, 2l+1; one row
+        // of the box is 128 contiguous (unit-permuted) bytes, so every warp-wide read is conflict-free
+        const uint32_t u = (uint32_t)lane >> 2, sub = ((uint32_t)lane & 3u) * 4u;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+        for (uint32_t r = 0; r < 32; ++r) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(box + r * 128u + ((u ^ (r & 7u)) * 16u) + sub) : "memory");
+          s0 += __uint_as_float(w << 16);
+          s1 += __uint_as_float(w & 0xffff0000u);
+        }
+        const int64_t col = gcol0 + 2 * lane;
+        if (col + 1 < N) {
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ep.colsum + col), "f"(s0), "f"(s1) : "memory");
+        } else if (col < N) {
+          atomicAdd(ep.colsum + col, s0);
+        }
       }
       ++n_stores;
     }
@@ -844,11 +871,9 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t col
 // bf16 outputs with a TMA-compatible pitch leave through shared memory + bulk tensor stores: map over C [M, N] with
 // [32 rows x 64 cols] SWIZZLE_128B boxes.  LSTC_GEMM_TMA_STORE=0 keeps the register stores (A/B measurements).
 static int make_tmap_c(CUtensorMap* tc, EpilogueParams& ep, int64_t M, int64_t N) {
-  const char* e = getenv("LSTC_GEMM_TMA_STORE");  // read per call: A/B measurements flip it inside one process
-  const bool enabled = !(e != nullptr && e[0] == '0');
   memset(tc, 0, sizeof(*tc));
   ep.tma_store = 0;
-  if (!enabled || ep.c_is_f32 || ep.ldc % 8 != 0 || N < 64 || M < 32) return LSTC_OK;
+  if (lstc_gemm_bf16_fuses_colsum(M, N, ep.ldc, ep.c_is_f32) == 0) return LSTC_OK;  // same condition: TMA-store path
   const uint64_t gdim[2] = {(uint64_t)N, (uint64_t)M};
   const uint64_t gstride[1] = {(uint64_t)ep.ldc * 2};
   const uint32_t box[2] = {64u, 32u};
@@ -955,11 +980,22 @@ static int dispatch_major(int a_mn, int b_mn, const void* A, int64_t lda, const 
 
 using namespace lstc;
 
+static bool tma_store_enabled() {
+  const char* e = getenv("LSTC_GEMM_TMA_STORE");  // read per call: A/B measurements flip it inside one process
+  return !(e != nullptr && e[0] == '0');
+}
+
+// 1 when lstc_gemm_bf16 can add the column sums of C to `colsum` in its epilogue for this output (bf16 C on the TMA-store
+// path), 0 when the caller has to run a separate column-sum pass
+extern "C" int lstc_gemm_bf16_fuses_colsum(int64_t M, int64_t N, int64_t ldc, int c_is_f32) {
+  return (tma_store_enabled() && !c_is_f32 && ldc % 8 == 0 && N >= 64 && M >= 32) ? 1 : 0;
+}
+
 extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                               int b_mn_major, int64_t M, int64_t N, int64_t K, void* C, int64_t ldc,
                               int c_is_f32, const float* bias, int relu, const void* relu_mask, int64_t ld_mask,
                               const void* residual, int64_t ld_res, float dropout_p, uint64_t seed,
-                              uint64_t offset, int split_k, int accumulate, void* stream_) {
+                              uint64_t offset, int split_k, int accumulate, float* colsum, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LSTC_CHECK_ARG(A && B && C, "lstc_gemm_bf16: null operand");
   LSTC_CHECK_ARG(M > 0 && N > 0 && K > 0, "lstc_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M,
@@ -975,6 +1011,9 @@ extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   LSTC_CHECK_ARG(!(split_k > 1) || (!bias && !relu && !relu_mask && !residual && dropout_p == 0.f),
                  "lstc_gemm_bf16: split-K supports no fused epilogue");
   LSTC_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "lstc_gemm_bf16: dims exceed int32");
+  LSTC_CHECK_ARG(colsum == nullptr || lstc_gemm_bf16_fuses_colsum(M, N, ldc, c_is_f32) != 0,
+                 "lstc_gemm_bf16: fused column sums need a bf16 C with ldc %% 8 == 0, M >= 32, N >= 64 (TMA-store epilogue)");
+  LSTC_CHECK_ARG(colsum == nullptr || ((uintptr_t)colsum % 8 == 0), "lstc_gemm_bf16: colsum must be 8-byte aligned");
 
   gemm::EpilogueParams ep;
   ep.C = C;
@@ -987,6 +1026,8 @@ extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   ep.ld_mask = ld_mask;
   ep.residual = (const __nv_bfloat16*)residual;
   ep.ld_res = ld_res;
+  ep.colsum = colsum;
+  ep.tma_store = 0;
   ep.drop_p = dropout_p;
   ep.drop_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
   ep.drop_thr16 = dropout_threshold16(dropout_p);

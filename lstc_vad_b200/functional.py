@@ -478,11 +478,15 @@ class FFNBlockFn(torch.autograd.Function):
             gin = gy2d if gy2d is not None else gy2
             db2 = ops.colsum(gin)
         dw2 = _wgrad(gin, h)                                                  # [D, Dh+pad]
+        # d b_1 = column sums of dh: accumulated by the product's epilogue from the staged bf16 tile where it can
+        fused = ops.gemm_fuses_colsum(gin.shape[0], Dh + pad)
+        db1 = torch.zeros(Dh + pad, device=gin.device, dtype=F32) if fused else None
         if pad == 0:
-            dh = _dgrad(gin, w2, relu_mask=h)                                 # [M, Dh]
+            dh = _dgrad(gin, w2, relu_mask=h, colsum_out=db1)                 # [M, Dh]
         else:
-            dh = ops.gemm(gin, CACHE.bf16(w2, pad_cols=pad), b_mn=True, relu_mask=h)   # [M, Dh+pad]
-        db1 = ops.colsum(dh)
+            dh = ops.gemm(gin, CACHE.bf16(w2, pad_cols=pad), b_mn=True, relu_mask=h, colsum_out=db1)   # [M, Dh+pad]
+        if not fused:
+            db1 = ops.colsum(dh)
         dw1 = _wgrad(dh, x2)                                                  # [Dh+pad, D]
         gx = None
         if ctx.needs_input_grad[0]:

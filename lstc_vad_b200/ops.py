@@ -84,11 +84,18 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> int:
 
 
 # ------------------------------------------------------------------------------------------ GEMM
+def gemm_fuses_colsum(M: int, N: int, ldc: Optional[int] = None, out_dtype=BF16) -> bool:
+    """True when `gemm(..., colsum_out=...)` can add the column sums of its bf16 output in the epilogue."""
+    return bool(_lib.load().lstc_gemm_bf16_fuses_colsum(int(M), int(N), int(N if ldc is None else ldc), int(out_dtype == F32)))
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out_dtype=BF16,
          bias: Optional[torch.Tensor] = None, relu: bool = False, relu_mask: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, dropout: Dropout = NO_DROPOUT, split_k: int = 1,
-         out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """C[M,N] = epilogue(A @ B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn); bf16."""
+         out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         colsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[M,N] = epilogue(A @ B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn); bf16.
+    colsum_out (fp32 [N]): += column sums of the stored bf16 C, fused into the epilogue (see gemm_fuses_colsum)."""
     lib = _lib.load()
     _cuda(a, "a", BF16)
     _cuda(b, "b", BF16)
@@ -117,6 +124,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if residual is not None:
         _cuda(residual, "residual", BF16)
         ld_res = _rowmajor2d(residual, "residual")
+    if colsum_out is not None:
+        _cuda(colsum_out, "colsum_out", F32)
+        if colsum_out.numel() != N or not colsum_out.is_contiguous():
+            raise RuntimeError("lstc_vad_b200.gemm: colsum_out must be a contiguous fp32 [N] vector")
     p, seed, off = dropout
     prof = PROFILE.enabled
     if prof:
@@ -124,7 +135,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         e0.record()
     st = lib.lstc_gemm_bf16(_p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), M, N, K, _p(out), ldc,
                             int(out.dtype == F32), _p(bias), int(relu), _p(relu_mask), ld_mask, _p(residual), ld_res,
-                            float(p), int(seed), int(off), int(split_k), int(accumulate), _stream())
+                            float(p), int(seed), int(off), int(split_k), int(accumulate), _p(colsum_out), _stream())
     if prof:
         e1.record()
         kind = ("mn" if a_mn else "k") + "-" + ("mn" if b_mn else "k")

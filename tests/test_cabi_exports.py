@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol_and_signatures_match():
     from lstc_vad_b200 import _lib, build
     build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
     lib = _lib.load()
-    assert lib.lstc_abi_version() == 1
+    assert lib.lstc_abi_version() == 2
     decls = header_decls()
     assert set(decls) == set(_lib.SIGNATURES), set(decls) ^ set(_lib.SIGNATURES)
     cmap = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "i64",
@@ -60,7 +60,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     """Argument validation happens before any CUDA call, so it can be exercised on the CPU box."""
     from lstc_vad_b200 import _lib
     lib = _lib.load()
-    st = lib.lstc_gemm_bf16(None, 8, 0, None, 8, 0, 1, 1, 1, None, 8, 0, None, 0, None, 0, None, 0, 0.0, 0, 0, 1, 0, None)
+    st = lib.lstc_gemm_bf16(None, 8, 0, None, 8, 0, 1, 1, 1, None, 8, 0, None, 0, None, 0, None, 0, 0.0, 0, 0, 1, 0, None, None)
     assert st == 1 and b"null operand" in lib.lstc_last_error()
     st = lib.lstc_layernorm_fwd(1, 0, 1, 1, 1, 0, 1, 1, 4, 12, 1e-6, None)
     assert st == 1 and b"multiple of 8" in lib.lstc_last_error()

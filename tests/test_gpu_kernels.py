@@ -83,6 +83,17 @@ def test_gemm_bf16_out_all_shapes(ops, M, N, K):
     ops.gemm(a, b, bias=bias, relu_mask=mask, residual=res, out=wide[:, 8:8 + N])
     assert torch.equal(wide[:, 8:8 + N], got)
     assert (wide[:, :8] == 7).all() and (wide[:, 8 + N:] == 7).all()
+    # column sums of the stored bf16 values, accumulated in the epilogue (d b_1 of the FFN backward) on top of `colsum_out`
+    if ops.gemm_fuses_colsum(M, N):
+        cs = torch.full((N,), 0.5, device="cuda", dtype=F32)
+        got2 = ops.gemm(a, b, bias=bias, relu_mask=mask, residual=res, colsum_out=cs)
+        assert torch.equal(got2, got)
+        want = got.float().sum(0) + 0.5
+        assert_close(f"gemm fused colsum {M}x{N}x{K}", cs, want, rtol=1e-4, atol=1e-3 * math.sqrt(M))
+    else:
+        assert N < 64 or M < 32
+        with pytest.raises(RuntimeError):
+            ops.gemm(a, b, colsum_out=torch.zeros(N, device="cuda"))
 
 
 def test_gemm_epilogue_bias_relu_residual(ops):
