@@ -33,12 +33,12 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // one 128-byte swizzle atom of bf16 along the reduction dim
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;     // 6 warps
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_THREADS = 320;     // 10 warps: TMA producer, MMA issuer, 8 epilogue warps
+constexpr int NUM_EPI_WARPS = 8;     // two per TMEM lane quarter (= two per SM sub-partition), each draining half of the columns
 constexpr uint32_t SMEM_BUDGET = 192 * 1024;  // operand ring
-// epilogue staging for the TMA-store path: per epilogue warp two [32 rows x 64 cols] bf16 boxes (128-byte rows, SWIZZLE_128B)
+// epilogue staging for the TMA-store path: per epilogue warp one [32 rows x 64 cols] bf16 box (128-byte rows, SWIZZLE_128B)
 constexpr uint32_t EPI_BOX_BYTES = 32 * 128;
-constexpr uint32_t EPI_STAGE_BYTES = NUM_EPI_WARPS * 2 * EPI_BOX_BYTES;  // 32 KB
+constexpr uint32_t EPI_STAGE_BYTES = NUM_EPI_WARPS * EPI_BOX_BYTES;  // 32 KB
 
 struct EpilogueParams {
   void* C;                 // bf16 or fp32 [M, N]
@@ -439,14 +439,15 @@ __device__ __forceinline__ void epilogue_store_direct(const EpilogueParams& ep, 
   }
 }
 
-// Drains one accumulator tile: rows [row0_warp, row0_warp + 32) of this warp (thread = row0_warp + lane), BN columns from
-// n0.  `tmem_tile` = TMEM address of this warp's lane quarter at the accumulator stage's first column; `stage_smem` = this
-// warp's two staging boxes; `n_stores` counts the warp's bulk stores (selects the staging box).
-template <int BN>
+// Drains this warp's part of one accumulator tile: rows [row0_warp, row0_warp + 32) (thread = row0_warp + lane), NC columns
+// from n0.  `tmem_tile` = TMEM address of this warp's lane quarter at its first accumulator column; `box` = this warp's
+// staging box.  Eight epilogue warps share a tile (two per lane quarter, half of the columns each): with one warp per SM
+// sub-partition the dependent chains of the epilogue math (Philox rounds, bf16 unpack / select / pack) were issue-latency
+// bound and the dropout epilogues could not keep up with the MMAs of the next tile (tensor pipe 74 % active).
+template <int NC>
 __device__ __forceinline__ void drain_tile(const EpilogueParams& ep, const CUtensorMap* tmap_c, uint32_t tmem_tile,
                                            uint32_t full_bar, uint32_t full_parity, int64_t row0_warp, int64_t n0,
-                                           int64_t M, int64_t N, bool has_k, uint32_t stage_smem, uint32_t& n_stores,
-                                           int lane) {
+                                           int64_t M, int64_t N, bool has_k, uint32_t box, int lane) {
   const int64_t row = row0_warp + lane;
   const bool tma = ep.tma_store != 0;
   ChunkAux cur, nxt;
@@ -455,19 +456,17 @@ __device__ __forceinline__ void drain_tile(const EpilogueParams& ep, const CUten
   aux_prefetch(ep, row, n0, M, N, cur);
   mbar_wait(full_bar, full_parity);
   tcgen05_fence_after();
-  uint32_t box = stage_smem + (n_stores & 1u) * EPI_BOX_BYTES;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = 0; c < NC / 32; ++c) {
     const int64_t col0 = n0 + c * 32;
     if (col0 >= N) break;  // warp-uniform
-    if (c + 1 < BN / 32) aux_prefetch(ep, row, col0 + 32, M, N, nxt);
+    if (c + 1 < NC / 32) aux_prefetch(ep, row, col0 + 32, M, N, nxt);
     uint32_t r[32];
     tmem_ld_32x32b_x32(tmem_tile + c * 32, r);
     tmem_ld_wait();
     if (tma && (c & 1) == 0) {
-      // the box used two stores ago must have been read out of shared memory
-      box = stage_smem + (n_stores & 1u) * EPI_BOX_BYTES;
-      if (lane == 0) tma_wait_group_read<1>();
+      // the previous bulk store of this warp must have read the box out of shared memory
+      if (lane == 0) tma_wait_group_read<0>();
       __syncwarp();
     }
     if (row < M) {
@@ -510,9 +509,9 @@ __device__ __forceinline__ void drain_tile(const EpilogueParams& ep, const CUten
         const uint32_t u = (uint32_t)lane >> 2, sub = ((uint32_t)lane & 3u) * 4u;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-        for (uint32_t r = 0; r < 32; ++r) {
+        for (uint32_t rr = 0; rr < 32; ++rr) {
           uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(box + r * 128u + ((u ^ (r & 7u)) * 16u) + sub) : "memory");
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(box + rr * 128u + ((u ^ (rr & 7u)) * 16u) + sub) : "memory");
           s0 += __uint_as_float(w << 16);
           s1 += __uint_as_float(w & 0xffff0000u);
         }
@@ -523,7 +522,6 @@ __device__ __forceinline__ void drain_tile(const EpilogueParams& ep, const CUten
           atomicAdd(ep.colsum + col, s0);
         }
       }
-      ++n_stores;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -542,6 +540,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const __grid_constant__ CUtensorMap tmap_c, int64_t M, int64_t N, int64_t K, int splits, EpilogueParams ep) {
   using Cfg = Config<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EPI_SPLIT = (BN >= 128) ? 2 : 1;  // epilogue warps per lane quarter (a warp drains >= one 64-column box)
+  constexpr int EPI_COLS = BN / EPI_SPLIT;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -575,7 +575,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);
+      mbar_init(tmem_empty_bar(a), 4 * EPI_SPLIT);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -654,26 +654,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
-    const uint32_t stage_smem = epi_smem + (uint32_t)q * 2u * EPI_BOX_BYTES;
-    uint32_t n_stores = 0;
-    uint32_t it = 0;
-    for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
-      const int64_t tile = wi % (tiles_m * tiles_n);
-      const int64_t split = wi / (tiles_m * tiles_n);
-      const int64_t m0 = (ep.n_major ? tile % tiles_m : tile / tiles_n) * BLOCK_M;
-      const int64_t n0 = (ep.n_major ? tile / tiles_m : tile % tiles_n) * BN;
-      const int64_t kb0 = split * kb_per_split;
-      const bool has_k = kb0 < num_kb_total;  // an empty split contributes nothing
-      const uint32_t acc = it & 1u;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      drain_tile<BN>(ep, &tmap_c, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, tmem_full_bar(acc), acc_phase,
-                     m0 + q * 32, n0, M, N, has_k, stage_smem, n_stores, lane);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+    const int q = warp_idx & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp_idx - 2) >> 2;  // which part of the tile's columns
+    if (half < EPI_SPLIT) {
+      const uint32_t box = epi_smem + (uint32_t)(warp_idx - 2) * EPI_BOX_BYTES;
+      uint32_t it = 0;
+      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
+        const int64_t tile = wi % (tiles_m * tiles_n);
+        const int64_t split = wi / (tiles_m * tiles_n);
+        const int64_t m0 = (ep.n_major ? tile % tiles_m : tile / tiles_n) * BLOCK_M;
+        const int64_t n0 = (ep.n_major ? tile / tiles_m : tile % tiles_n) * BN + half * EPI_COLS;
+        const int64_t kb0 = split * kb_per_split;
+        const bool has_k = kb0 < num_kb_total;  // an empty split contributes nothing
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        drain_tile<EPI_COLS>(ep, &tmap_c, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * EPI_COLS,
+                             tmem_full_bar(acc), acc_phase, m0 + q * 32, n0, M, N, has_k, box, lane);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      }
+      if (lane == 0) tma_wait_group_all();  // bulk stores still reading shared memory / in flight
     }
-    if (lane == 0) tma_wait_group_all();  // bulk stores still reading shared memory / in flight
   }
 
   // teardown
@@ -707,6 +709,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   using Cfg = Config2<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF_N = BN / 2;
+  constexpr int EPI_COLS = BN / 2;  // two epilogue warps per lane quarter
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_smem = smem_base + STAGES * Cfg::STAGE_BYTES;  // TMA-store staging boxes
@@ -743,7 +746,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 2 * NUM_EPI_WARPS);  // leader's copy: epilogue warps of both CTAs
+      mbar_init(tmem_empty_bar(a), 2 * NUM_EPI_WARPS);  // leader's copy: the 8 epilogue warps of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -826,25 +829,27 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   } else {
     // ===================== epilogue warps (both CTAs; each drains its own 128 TMEM lanes) =====================
     const int q = warp_idx & 3;
-    const uint32_t stage_smem = epi_smem + (uint32_t)q * 2u * EPI_BOX_BYTES;
-    uint32_t n_stores = 0;
-    uint32_t it = 0;
-    for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters, ++it) {
-      const int64_t tile = wi % (tiles_m * tiles_n);
-      const int64_t split = wi / (tiles_m * tiles_n);
-      const int64_t m0 = (ep.n_major ? tile % tiles_m : tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M;
-      const int64_t n0 = (ep.n_major ? tile / tiles_m : tile % tiles_n) * BN;
-      const int64_t kb0 = split * kb_per_split;
-      const bool has_k = kb0 < num_kb_total;
-      const uint32_t acc = it & 1u;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      drain_tile<BN>(ep, &tmap_c, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, tmem_full_bar(acc), acc_phase,
-                     m0 + q * 32, n0, M, N, has_k, stage_smem, n_stores, lane);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+    const int half = (warp_idx - 2) >> 2;
+    {
+      const uint32_t box = epi_smem + (uint32_t)(warp_idx - 2) * EPI_BOX_BYTES;
+      uint32_t it = 0;
+      for (int64_t wi = cluster_id; wi < num_work; wi += num_clusters, ++it) {
+        const int64_t tile = wi % (tiles_m * tiles_n);
+        const int64_t split = wi / (tiles_m * tiles_n);
+        const int64_t m0 = (ep.n_major ? tile % tiles_m : tile / tiles_n) * (2 * BLOCK_M) + rank * BLOCK_M;
+        const int64_t n0 = (ep.n_major ? tile / tiles_m : tile % tiles_n) * BN + half * EPI_COLS;
+        const int64_t kb0 = split * kb_per_split;
+        const bool has_k = kb0 < num_kb_total;
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        drain_tile<EPI_COLS>(ep, &tmap_c, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * EPI_COLS,
+                             tmem_full_bar(acc), acc_phase, m0 + q * 32, n0, M, N, has_k, box, lane);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+      }
+      if (lane == 0) tma_wait_group_all();
     }
-    if (lane == 0) tma_wait_group_all();
   }
 
   // teardown: nobody may free TMEM / exit while the peer can still signal or read

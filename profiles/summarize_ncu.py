@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Turns an .ncu-rep (ncu --set full) into a compact per-launch table of the metrics DESIGN.md / bench.py quote.
-    python profiles/summarize_ncu.py gpurun_out/x.ncu-rep > profiles/x_summary.txt
+    python profiles/summarize_ncu.py gpurun_out/x.ncu-rep [more ...] > profiles/x_summary.txt
+A `.csv` argument is taken as the output of `ncu -i x.ncu-rep --page raw --csv` (made on the GPU box, where the report
+itself is too large to bring back).
 """
 import csv
 import subprocess
@@ -18,8 +20,14 @@ WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
 
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
+    if len(rows) < 3:
+        print("# " + path + ": no kernel rows")
+        return
     hdr, units = rows[0], rows[1]
     cols = [(hdr.index(m), n, units[hdr.index(m)]) for m, n in WANT if m in hdr]
     ki = hdr.index("Kernel Name")
@@ -37,4 +45,5 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    for a in sys.argv[1:]:
+        main(a)

@@ -1,17 +1,22 @@
 #!/bin/bash
-# Round-end evidence on one B200: launch list (+ DRAM traffic) of one train step, ncu --set full of one launch of each
-# attention kernel, the stand-alone kernel timings, compute-sanitizer over the attention unit tests, and the bench line.
+# Round-end evidence on one B200 (prefix $1, default r2f; $2 = "tests" also runs every GPU test first): the bench line of
+# the headline and of the other workloads, the launch list (+ DRAM traffic) of one train step, stand-alone kernel timings.
+# The ncu --set full captures are separate (tools/gpu_ncu_kernels.sh): gpurun brings back at most 64 MiB.
+P=${1:-r2f}
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r2_launches_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-extras > gpurun_out/r2_ncu_bench.log 2>&1
-echo "launch list exit $?"
-for spec in "fwd49 49 attn_fwd" "bwd49 49 attn_bwd" "fwd81 81 attn_fwd" "bwd81 81 attn_bwd" "bwd19 19 attn_bwd"; do
-  set -- $spec
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc" -s 3 -c 1 -o gpurun_out/r2_attn_$1 -f python tools/kernel_bench.py --reps 1 --L $2 --only "$3 dropout" > /dev/null 2>&1
-  echo "ncu $1 exit $?"
+O=gpurun_out/$P
+if [ "$2" = "tests" ]; then
+  timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > ${O}_tests.log 2>&1; echo "gpu tests exit $?" | tee ${O}_summary.txt; tail -3 ${O}_tests.log | cut -c1-200
+fi
+timeout 900 python bench.py > ${O}_bench_default.log 2>&1; echo "bench exit $?" | tee -a ${O}_summary.txt; tail -1 ${O}_bench_default.log | cut -c1-200
+timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > ${O}_bench_reference.log 2>&1; echo "reference arm exit $?" | tee -a ${O}_summary.txt
+for wl in ltn_ubnormal ltn_ucf stn_sht; do
+  timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-extras > ${O}_wl_$wl.log 2>&1; echo "bench $wl exit $?" | tee -a ${O}_summary.txt
 done
-for l in 49 81 19 17; do timeout 300 python tools/kernel_bench.py --L $l --only attn; done > gpurun_out/r2_kernel_bench_attn.txt 2>&1
-timeout 300 python tools/kernel_bench.py --only ln >> gpurun_out/r2_kernel_bench_attn.txt 2>&1
-timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attn_fwd or attn_bwd or attn_dropout" -p no:cacheprovider > gpurun_out/r2_sanitizer_memcheck.log 2>&1
-echo "memcheck exit $?"; tail -3 gpurun_out/r2_sanitizer_memcheck.log
-timeout 900 python bench.py > gpurun_out/r2_bench_default.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/r2_bench_default.log | cut -c1-300
-ls -la gpurun_out/r2_attn_*.ncu-rep
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file ${O}_launches_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-extras > ${O}_ncu_bench.log 2>&1
+echo "launch list exit $?" | tee -a ${O}_summary.txt
+for l in 49 81 19 17; do timeout 300 python tools/kernel_bench.py --L $l --only attn; done > ${O}_kernel_bench.txt 2>&1
+timeout 300 python tools/kernel_bench.py --only ln >> ${O}_kernel_bench.txt 2>&1
+timeout 300 python tools/gemm_bench.py --reps 20 > ${O}_gemm_bench.txt 2>&1
+cat ${O}_summary.txt
+du -sh gpurun_out
