@@ -356,6 +356,20 @@ def auc_delta_vs_oracle(wl, dev, train_steps: int = 12, test_windows: int = 384,
                     "AUC is closest to 0.97, every checkpoint listed"}
 
 
+def committed_gemm_traffic(workload: str):
+    """Mean DRAM bytes per GEMM launch of one LTN-SHT step, read from the committed ncu launch list of this same command
+    (profiles/r2_step_launches_traffic.txt, last line); None for the other workloads or when the file is absent."""
+    if workload != "ltn_sht":
+        return None
+    try:
+        import re
+        tail = (ROOT / "profiles" / "r2_step_launches_traffic.txt").read_text().strip().splitlines()[-1]
+        m = re.search(r"mean DRAM traffic per launch ([0-9.]+) GB", tail)
+        return float(m.group(1)) * 1e9 if m else None
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -739,7 +753,7 @@ def main():
                          # mean dram__bytes_read+write per GEMM launch over the 40 launches of one step: NOT measurable
                          # in-run (needs ncu); taken from the committed capture of this same command,
                          # profiles/r2_step_launches_traffic.txt (algorithmic operand+result bytes average 0.80 GB)
-                         "traffic": 0.983e9, "traffic_unit": "bytes/launch (mean of 40 launches)",
+                         "traffic": committed_gemm_traffic(wl.name), "traffic_unit": "bytes/launch (mean of 40 launches)",
                          "traffic_source": "profiles/r2_step_launches_traffic.txt (ncu dram__bytes_read.sum + "
                                            "dram__bytes_write.sum of `bench.py --steps 1 --warmup 3 --no-graph`)",
                          "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM launches of the pass)",
