@@ -18,5 +18,7 @@ echo "launch list exit $?" | tee -a ${O}_summary.txt
 for l in 49 81 19 17; do timeout 300 python tools/kernel_bench.py --L $l --only attn; done > ${O}_kernel_bench.txt 2>&1
 timeout 300 python tools/kernel_bench.py --only ln >> ${O}_kernel_bench.txt 2>&1
 timeout 300 python tools/gemm_bench.py --reps 20 > ${O}_gemm_bench.txt 2>&1
+timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm" -p no:cacheprovider > ${O}_sanitizer_gemm.log 2>&1
+echo "memcheck gemm exit $?" | tee -a ${O}_summary.txt; tail -3 ${O}_sanitizer_gemm.log | cut -c1-200
 cat ${O}_summary.txt
 du -sh gpurun_out

@@ -3,6 +3,7 @@
 # attention kernels at L = 49; the reports are turned into raw-metric CSVs on the box (gpurun brings back <= 64 MiB) and
 # summarised here with profiles/summarize_ncu.py --csv.
 P=${1:-r2f}
+WHAT=${2:-all}   # "gemm": only the GEMM captures
 mkdir -p gpurun_out /tmp/ncu
 O=gpurun_out/$P
 i=0
@@ -12,6 +13,7 @@ for c in "fwd ffn w1" "fwd ffn w2" "dgrad ffn w2" "dgrad ffn w1" "wgrad ffn w1" 
   echo "ncu gemm '$c' exit $?"
   ncu -i /tmp/ncu/gemm_$i.ncu-rep --page raw --csv > ${O}_ncu_gemm_$i.csv 2>/dev/null
 done
+if [ "$WHAT" = "gemm" ]; then ls -la ${O}_ncu_*.csv; exit 0; fi
 for spec in "fwd49 49 attn_fwd" "bwd49 49 attn_bwd" "fwd81 81 attn_fwd" "bwd81 81 attn_bwd"; do
   set -- $spec
   timeout 600 ncu --set full --clock-control none -k regex:"attn_tc" -s 3 -c 1 -o /tmp/ncu/attn_$1 -f python tools/kernel_bench.py --reps 1 --L $2 --only "$3 dropout" > /dev/null 2>&1
