@@ -11,7 +11,7 @@ python profiles/summarize_launches.py ${G}_launches_traffic.csv > profiles/r2_st
 } > profiles/r2_ncu_gemm_summary.txt
 {
   echo "# ncu --set full --clock-control none, one launch each, tools/gpu_ncu_kernels.sh: tcgen05 attention at L = 49 / 81 (dropout + rel-pos bias), LayerNorm at 62,720 x 2048"
-  python profiles/summarize_ncu.py ${G}_ncu_attn_*.csv ${G}_ncu_ln_*.csv
+  python profiles/summarize_ncu.py $(ls ${G}_ncu_attn_*.csv ${G}_ncu_ln_*.csv 2>/dev/null || ls gpurun_out/r2m_ncu_attn_*.csv gpurun_out/r2m_ncu_ln_*.csv)
 } > profiles/r2_ncu_attention_summary.txt
 {
   echo "# tools/kernel_bench.py --L {49,81,19,17} --only attn ; --only ln  (one B200, CUDA events, L2 flushed between repetitions; 1280 windows, 8 heads x 256; HBM peak = MEASURED_PEAKS.json hbm_gbs 6544 GB/s)"
