@@ -68,6 +68,24 @@ def test_argument_errors_are_reported_without_a_gpu():
         _lib.check(st, "lstc_layernorm_fwd")
 
 
+def test_gemm_colsum_capability_query_is_pure_host_logic(monkeypatch):
+    """lstc_gemm_bf16_fuses_colsum: bf16 C, 16-byte pitch, at least one [32 x 64] store box - and the same answer decides
+    whether lstc_gemm_bf16 accepts a colsum pointer (checked before any CUDA call)."""
+    from lstc_vad_b200 import _lib
+    lib = _lib.load()
+    monkeypatch.delenv("LSTC_GEMM_TMA_STORE", raising=False)
+    assert lib.lstc_gemm_bf16_fuses_colsum(62720, 4096, 4096, 0) == 1
+    assert lib.lstc_gemm_bf16_fuses_colsum(62720, 4096, 4096, 1) == 0     # fp32 C
+    assert lib.lstc_gemm_bf16_fuses_colsum(62720, 3027, 3027, 0) == 0     # pitch not a multiple of 8 elements
+    assert lib.lstc_gemm_bf16_fuses_colsum(62720, 32, 32, 0) == 0         # narrower than one store box
+    assert lib.lstc_gemm_bf16_fuses_colsum(16, 4096, 4096, 0) == 0        # shorter than one store box
+    # a colsum pointer with an output the epilogue cannot fuse it for is an argument error, not a silent skip
+    st = lib.lstc_gemm_bf16(16, 8, 0, 16, 8, 0, 64, 32, 64, 16, 32, 0, None, 0, None, 0, None, 0, 0.0, 0, 0, 1, 0, 16, None)
+    assert st == 1 and b"fused column sums" in lib.lstc_last_error()
+    monkeypatch.setenv("LSTC_GEMM_TMA_STORE", "0")                        # register-store epilogue: no staged tile to sum
+    assert lib.lstc_gemm_bf16_fuses_colsum(62720, 4096, 4096, 0) == 0
+
+
 def test_product_package_never_imports_the_oracle():
     for py in (ROOT / "lstc_vad_b200").rglob("*.py"):
         src = py.read_text()
