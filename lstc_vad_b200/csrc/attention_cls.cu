@@ -267,6 +267,7 @@ static int fill(Params& p, const void* q, int64_t ld_q, const void* k, const voi
   LSTC_CHECK_ARG(dk == 64 || dk == 128 || dk == 256, "attn_cls: d_k=%d unsupported (64, 128 or 256)", dk);
   LSTC_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0, "attn_cls: leading dims must be multiples of 8");
   LSTC_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_cls: dropout_p out of range");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(q) && LSTC_ALIGNED16(k) && LSTC_ALIGNED16(v), "attn_cls: q, k, v must be 16-byte aligned");
   p.q = (const __nv_bfloat16*)q; p.ld_q = ld_q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
   p.ld_kv = ld_kv; p.W = W; p.L = L; p.H = H; p.scale = scale; p.drop_p = drop_p;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f; p.drop_thr16 = dropout_threshold16(drop_p);
@@ -293,7 +294,7 @@ extern "C" int lstc_attn_cls_fwd(const void* q, int64_t ld_q, const void* k, con
   attn_cls::Params p{};
   int rc = attn_cls::fill(p, q, ld_q, k, v, ld_kv, W, L, H, dk, scale, dropout_p, seed, offset);
   if (rc != LSTC_OK) return rc;
-  LSTC_CHECK_ARG(out != nullptr && ld_out % 8 == 0, "lstc_attn_cls_fwd: bad output");
+  LSTC_CHECK_ARG(out != nullptr && ld_out % 8 == 0 && LSTC_ALIGNED16(out), "lstc_attn_cls_fwd: bad output");
   if (W == 0) return LSTC_OK;
   p.out = (__nv_bfloat16*)out; p.ld_out = ld_out;
   const unsigned g = attn_cls::grid_for(W, H);
@@ -314,6 +315,8 @@ extern "C" int lstc_attn_cls_bwd(const void* q, int64_t ld_q, const void* k, con
   if (rc != LSTC_OK) return rc;
   LSTC_CHECK_ARG(dout && dq && dk_out && dv_out, "lstc_attn_cls_bwd: null pointer");
   LSTC_CHECK_ARG(ld_do % 8 == 0 && ld_dq % 8 == 0 && ld_dkv % 8 == 0, "lstc_attn_cls_bwd: leading dims must be multiples of 8");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(dout) && LSTC_ALIGNED16(dq) && LSTC_ALIGNED16(dk_out) && LSTC_ALIGNED16(dv_out),
+                 "lstc_attn_cls_bwd: dout, dq, dk, dv must be 16-byte aligned");
   if (W == 0) return LSTC_OK;
   p.dout = (const __nv_bfloat16*)dout; p.ld_do = ld_do; p.out = (__nv_bfloat16*)dq; p.ld_out = ld_dq;
   p.dk = (__nv_bfloat16*)dk_out; p.dv = (__nv_bfloat16*)dv_out; p.ld_dkv = ld_dkv;
@@ -330,6 +333,7 @@ extern "C" int lstc_add_rows_bf16(void* dst, int64_t ld_dst, const void* src, in
                                   int64_t cols, void* stream) {
   LSTC_CHECK_ARG(dst && src, "lstc_add_rows_bf16: null pointer");
   LSTC_CHECK_ARG(cols % 8 == 0 && ld_dst % 8 == 0 && ld_src % 8 == 0, "lstc_add_rows_bf16: cols / lds must be multiples of 8");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(dst) && LSTC_ALIGNED16(src), "lstc_add_rows_bf16: dst, src must be 16-byte aligned");
   if (rows * cols == 0) return LSTC_OK;
   int64_t g = (rows * (cols / 8) + 255) / 256;
   if (g > (int64_t)num_sms() * 8) g = (int64_t)num_sms() * 8;

@@ -16,6 +16,8 @@ namespace lstc {
 
 void set_last_error(const char* fmt, ...);
 
+// every matrix operand is read / written with 16-byte vector accesses
+#define LSTC_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
 #define LSTC_CHECK_ARG(cond, ...)                                   \
   do {                                                              \
     if (!(cond)) {                                                  \

@@ -456,6 +456,8 @@ extern "C" int lstc_cls_prepend_fwd(const void* x, int x_is_f32, const float* cl
   LSTC_CHECK_ARG(x && out, "lstc_cls_prepend_fwd: null pointer");
   LSTC_CHECK_ARG(L0 >= 1 && D % 8 == 0 && D > 0, "lstc_cls_prepend_fwd: need L0 >= 1 and D %% 8 == 0");
   LSTC_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "lstc_cls_prepend_fwd: drop_p out of range");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(x) && LSTC_ALIGNED16(out) && LSTC_ALIGNED16(cls) && LSTC_ALIGNED16(pos),
+                 "lstc_cls_prepend_fwd: x, out, cls, pos must be 16-byte aligned");
   if (W == 0) return LSTC_OK;
   const int threads = 128;
   dim3 grid((unsigned)W, (unsigned)((D / 8 + threads - 1) / threads));
@@ -477,6 +479,7 @@ extern "C" int lstc_cls_prepend_bwd(const void* g, int cls_learned, float drop_p
   cudaStream_t stream = (cudaStream_t)stream_;
   LSTC_CHECK_ARG(g != nullptr, "lstc_cls_prepend_bwd: null pointer");
   LSTC_CHECK_ARG(L0 >= 1 && D % 8 == 0 && D > 0, "lstc_cls_prepend_bwd: need L0 >= 1 and D %% 8 == 0");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(g) && LSTC_ALIGNED16(dx), "lstc_cls_prepend_bwd: g, dx must be 16-byte aligned");
   if (dcls) LSTC_CHECK_CUDA(cudaMemsetAsync(dcls, 0, D * sizeof(float), stream));
   if (dpos) LSTC_CHECK_CUDA(cudaMemsetAsync(dpos, 0, (L0 + 1) * D * sizeof(float), stream));
   if (W == 0) return LSTC_OK;
@@ -503,6 +506,7 @@ extern "C" int lstc_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64
     return LSTC_OK;
   }
   LSTC_CHECK_ARG(x != nullptr, "lstc_colsum_bf16: null input");
+  LSTC_CHECK_ARG(ld % 8 != 0 || LSTC_ALIGNED16(x), "lstc_colsum_bf16: x must be 16-byte aligned when ld %% 8 == 0");
   const int parts = ew::colsum_parts(rows);
   dim3 grid((unsigned)((cols + 255) / 256), (unsigned)parts);
   ew::colsum_stage1_kernel<<<grid, dim3(32, 8), 0, stream>>>((const __nv_bfloat16*)x, rows, cols, ld,
@@ -519,6 +523,7 @@ extern "C" int lstc_dropout_apply_bf16(const void* x, void* y, int64_t rows, int
   LSTC_CHECK_ARG(x && y, "lstc_dropout_apply_bf16: null pointer");
   LSTC_CHECK_ARG(cols % 8 == 0, "lstc_dropout_apply_bf16: cols must be a multiple of 8");
   LSTC_CHECK_ARG(p >= 0.f && p < 1.f, "lstc_dropout_apply_bf16: p out of range");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(x) && LSTC_ALIGNED16(y), "lstc_dropout_apply_bf16: x, y must be 16-byte aligned");
   const int64_t n8 = rows * cols / 8;
   if (n8 == 0) return LSTC_OK;
   ew::dropout_apply_kernel<<<ew::grid_for(n8, 256), 256, 0, (cudaStream_t)stream>>>(

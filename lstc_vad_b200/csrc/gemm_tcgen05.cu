@@ -57,6 +57,7 @@ struct EpilogueParams {
   uint64_t seed, offset;
   int64_t drop_ld8;
   uint64_t policy_a, policy_b;  // L2 eviction priority of the A / B operand loads
+  int bias_vec, mask_vec, res_vec;  // 16-byte vector loads allowed (pointer 16-byte aligned, pitch a multiple of 8 elements)
   float* colsum;                // [N] fp32 or null: += column sums of the stored bf16 C (TMA-store path only)
   int tma_store;                // bf16 C leaves through shared memory + cp.async.bulk.tensor stores (tmap_c valid)
   int n_major;                  // tile order: 0 = consecutive work items sweep N first (a wave holds few M panels and all
@@ -316,12 +317,12 @@ struct ChunkAux {
 __device__ __forceinline__ void aux_prefetch(const EpilogueParams& ep, int64_t row, int64_t col0, int64_t M, int64_t N,
                                              ChunkAux& a) {
   if (row >= M || col0 + 32 > N) return;
-  if (ep.relu_mask != nullptr && (ep.ld_mask % 8 == 0)) {
+  if (ep.relu_mask != nullptr && ep.mask_vec) {
     const uint4* mp = reinterpret_cast<const uint4*>(ep.relu_mask + row * ep.ld_mask + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) a.mask[j] = __ldg(mp + j);
   }
-  if (ep.residual != nullptr && (ep.ld_res % 8 == 0)) {
+  if (ep.residual != nullptr && ep.res_vec) {
     const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + row * ep.ld_res + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) a.res[j] = __ldg(rp + j);
@@ -333,7 +334,7 @@ __device__ __forceinline__ void epilogue_math(const EpilogueParams& ep, float (&
                                               int64_t N, const ChunkAux& aux) {
   const bool full = (col0 + 32 <= N);
   if (ep.bias != nullptr) {
-    if (full) {
+    if (full && ep.bias_vec) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
@@ -350,7 +351,7 @@ __device__ __forceinline__ void epilogue_math(const EpilogueParams& ep, float (&
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (ep.relu_mask != nullptr) {
-    if (full && (ep.ld_mask % 8 == 0)) {
+    if (full && ep.mask_vec) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float f[8];
@@ -375,7 +376,7 @@ __device__ __forceinline__ void epilogue_math(const EpilogueParams& ep, float (&
     }
   }
   if (ep.residual != nullptr) {
-    if (full && (ep.ld_res % 8 == 0)) {
+    if (full && ep.res_vec) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float f[8];
@@ -1033,6 +1034,9 @@ extern "C" int lstc_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   ep.ld_res = ld_res;
   ep.colsum = colsum;
   ep.tma_store = 0;
+  ep.bias_vec = (bias != nullptr && (uintptr_t)bias % 16 == 0) ? 1 : 0;
+  ep.mask_vec = (relu_mask != nullptr && (uintptr_t)relu_mask % 16 == 0 && ld_mask % 8 == 0) ? 1 : 0;
+  ep.res_vec = (residual != nullptr && (uintptr_t)residual % 16 == 0 && ld_res % 8 == 0) ? 1 : 0;
   ep.drop_p = dropout_p;
   ep.drop_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
   ep.drop_thr16 = dropout_threshold16(dropout_p);

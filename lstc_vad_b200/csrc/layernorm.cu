@@ -547,6 +547,8 @@ extern "C" int lstc_layernorm_fwd(const void* x, int x_is_f32, const float* gamm
   LSTC_CHECK_ARG(D > 0 && D % 8 == 0 && D <= 8192, "lstc_layernorm_fwd: D=%lld must be a multiple of 8, <= 8192",
                  (long long)D);
   LSTC_CHECK_ARG(rows >= 0 && rows < (int64_t)2000000000, "lstc_layernorm_fwd: rows=%lld out of range", (long long)rows);
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(x) && LSTC_ALIGNED16(y) && LSTC_ALIGNED16(gamma) && LSTC_ALIGNED16(beta),
+                 "lstc_layernorm_fwd: x, y, gamma, beta must be 16-byte aligned");
   if (rows == 0) return LSTC_OK;
   int nv;
   const int threads = ln::threads_for(D, nv);
@@ -591,6 +593,9 @@ extern "C" int lstc_layernorm_bwd(const void* dy, int dy_is_f32, const void* x, 
                  (long long)D);
   LSTC_CHECK_ARG(rows >= 0 && rows < (int64_t)2000000000, "lstc_layernorm_bwd: rows=%lld out of range", (long long)rows);
   LSTC_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "lstc_layernorm_bwd: drop_p out of range");
+  LSTC_CHECK_ARG(LSTC_ALIGNED16(dy) && LSTC_ALIGNED16(x) && LSTC_ALIGNED16(dx) && LSTC_ALIGNED16(dx_drop) &&
+                     LSTC_ALIGNED16(gamma) && LSTC_ALIGNED16(workspace),
+                 "lstc_layernorm_bwd: dy, x, dx, dx_drop, gamma, workspace must be 16-byte aligned");
   if (rows == 0) {
     LSTC_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, D * sizeof(float), stream));
     LSTC_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, D * sizeof(float), stream));

@@ -96,6 +96,22 @@ def test_gemm_bf16_out_all_shapes(ops, M, N, K):
             ops.gemm(a, b, colsum_out=torch.zeros(N, device="cuda"))
 
 
+def test_gemm_epilogue_operands_at_odd_offsets(ops):
+    """mask / residual / bias views whose first element is not 16-byte aligned (column / element slices of wider buffers)
+    take the scalar-load path of the epilogue instead of faulting on a vector load."""
+    M, N, K = 200, 264, 128
+    a, b = _rand((M, K), 1.0, 51), _rand((N, K), 0.1, 52)
+    res_w, mask_w = _rand((M, N + 16), 1.0, 53), torch.relu(_rand((M, N + 16), 1.0, 54))
+    bias_w = _rand((N + 4,), 1.0, 55, F32)
+    for off in (1, 4, 8):
+        res, mask, bias = res_w[:, off:off + N], mask_w[:, off:off + N], bias_w[(off % 4):(off % 4) + N]
+        ref = (a.float() @ b.float().t() + bias) * (mask.float() > 0) + res.float()
+        got = ops.gemm(a, b, bias=bias, relu_mask=mask, residual=res, out_dtype=F32)
+        assert_close(f"gemm epilogue operands at element offset {off}", got, ref, rtol=1e-3, atol=1e-2)
+        got16 = ops.gemm(a, b, bias=bias, relu_mask=mask, residual=res)
+        assert_close(f"gemm epilogue operands at element offset {off} (bf16 out)", got16, ref, rtol=1e-2, atol=3e-2)
+
+
 def test_gemm_epilogue_bias_relu_residual(ops):
     M, N, K = 777, 1032, 520
     a, b = _rand((M, K), 1.0, 5), _rand((N, K), 0.05, 6)
