@@ -761,7 +761,10 @@ def main():
                          "measured": "CUDA-event pair around every GEMM launch during a second timed pass of the same K "
                                      "steps (ms_per_step of that pass: %.2f); the headline pass runs without per-launch "
                                      "events" % (ms_prof / steps),
-                         "by_operand_layout": by_kind, "model_tflops_whole_step": model_tflops},
+                         "by_operand_layout": by_kind, "model_tflops_whole_step": model_tflops,
+                         # FLOPs of the GEMM launches actually executed in one step (layer 1's input gradient is not
+                         # needed and not computed, so this is below the 3 x forward convention above) / headline time
+                         "executed_gemm_tflops_whole_step": (flops / steps) / (ms_head / steps * 1e-3) / 1e12 if flops else None},
             "clocks": (graph_clocks.summary() if (use_graph and graph_clocks is not None) else clocks.summary()),
         }
         # second roofline: the HBM-bound fused attention kernels (tcgen05 / TMEM), timed alone, against the measured copy rate
