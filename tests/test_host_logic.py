@@ -206,3 +206,31 @@ def test_dropin_package_shadows_the_reference_module_paths():
     env = dict(os.environ, PYTHONPATH=os.path.join(root, "dropin") + os.pathsep + root)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_wgrad_split_fills_the_last_wave_of_the_persistent_grid():
+    """Weight-gradient split-K plan (functional._wgrad_split): the persistent CTA-pair GEMM runs work items = output tiles x
+    splits in waves of 74 tile pairs, and the smallest split whose last wave is >= 95 % full is taken, with at least four
+    64-row k-blocks per split."""
+    from lstc_vad_b200.functional import _wgrad_split
+    rows = 1280 * 49
+    expected = {(2048, 2048): 8, (4096, 2048): 4, (2048, 4096): 4, (6144, 2048): 3}   # the four weight shapes of an LTN layer
+    for (n_out, k_out), s in expected.items():
+        assert _wgrad_split(n_out, k_out, rows) == s
+        tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)
+        items = tiles * s
+        assert items / (-(-items // 74) * 74) >= 0.95
+    # short reductions are never split below four k-blocks per split, tiny outputs use the single-CTA kernel's 148 units
+    assert _wgrad_split(2048, 2048, 256) == 1
+    assert 1 <= _wgrad_split(32, 512, 1280) <= (1280 // 64) // 4
+
+
+def test_bench_reads_the_committed_gemm_traffic_figure():
+    """`roofline.traffic` is the mean DRAM bytes per GEMM launch of the committed ncu launch list (not a constant in
+    bench.py), and only claimed for the workload that list was captured on."""
+    import bench
+    t = bench.committed_gemm_traffic("ltn_sht")
+    tail = (Path(__file__).resolve().parent.parent / "profiles" / "r2_step_launches_traffic.txt").read_text().strip().splitlines()[-1]
+    assert t is not None and f"{t / 1e9:.3f} GB" in tail
+    assert 0.8e9 <= t <= 1.3e9            # 0.80 GB algorithmic + the weight-gradient re-reads (DESIGN section 4)
+    assert bench.committed_gemm_traffic("stn_sht") is None
